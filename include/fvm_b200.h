@@ -1,0 +1,145 @@
+/* fvm_b200 -- C-ABI of the B200-native finite-volume assembly engine.
+ *
+ * The reference (meshpro/pyfvm) is pure Python and has no FFI; this header is
+ * the boundary a maintainer would bind (ctypes stub in INTEGRATION.md) to
+ * replace the numeric half of
+ *   pyfvm.discretize_linear(problem, mesh) -> (matrix, rhs)   [README.md:49]
+ *   f.eval(u)                                                 [README.md:121,136]
+ *   jacobian.get_linear_operator(u0)                          [README.md:116]
+ *   the norm inside pyfvm.newton                              [README.md:121]
+ * Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Conventions
+ *   - every call returns 0 on success, nonzero on error; fvm_last_error()
+ *     returns the message of the last failing call on this thread;
+ *   - handles are opaque pointers owned by the library until *_destroy;
+ *   - one ctx = one device + one CUDA stream; calls on a ctx are not
+ *     re-entrant; use one ctx per rank (one process per GPU);
+ *   - pointers named *_dev are device pointers valid on the ctx's device
+ *     (from fvm_dev_alloc or any other allocator, e.g. torch's data_ptr());
+ *     all other pointers are host pointers.
+ */
+#ifndef FVM_B200_H
+#define FVM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fvm_ctx fvm_ctx;
+typedef struct fvm_mesh fvm_mesh;
+typedef struct fvm_kernel fvm_kernel;
+
+/* Kernel modes: which numeric entry point of the reference a compiled functor
+ * set implements. */
+#define FVM_LINEAR 0   /* discretize_linear: CSR values + rhs   [README.md:49]  */
+#define FVM_RESIDUAL 1 /* f.eval(u)                             [README.md:121] */
+#define FVM_JACOBIAN 2 /* jacobian.get_linear_operator(u0)      [README.md:116] */
+
+/* fvm_kernel_create flags */
+#define FVM_KF_USES_EL 1u     /* edge functor reads edge_length              */
+#define FVM_KF_EDGE_MASKED 2u /* edge terms restricted to cell subdomains    */
+
+int fvm_version(void);
+const char* fvm_last_error(void);
+
+/* ---- context --------------------------------------------------------------*/
+int fvm_ctx_create(int device, fvm_ctx** out);
+int fvm_ctx_destroy(fvm_ctx* ctx);
+int fvm_ctx_sync(fvm_ctx* ctx);
+/* name, SM count, bytes of global memory of the ctx's device */
+int fvm_ctx_info(fvm_ctx* ctx, char* name, size_t name_len, int* sm_count, size_t* mem_bytes);
+
+/* ---- device / pinned memory (so a host binding needs no other GPU library) */
+int fvm_dev_alloc(fvm_ctx* ctx, size_t bytes, void** out_dev);
+int fvm_dev_free(fvm_ctx* ctx, void* ptr_dev);
+int fvm_dev_memset(fvm_ctx* ctx, void* ptr_dev, int value, size_t bytes);
+int fvm_h2d(fvm_ctx* ctx, void* dst_dev, const void* src, size_t bytes);
+int fvm_d2h(fvm_ctx* ctx, void* dst, const void* src_dev, size_t bytes);
+int fvm_host_alloc(fvm_ctx* ctx, size_t bytes, void** out); /* pinned */
+int fvm_host_free(fvm_ctx* ctx, void* ptr);
+
+/* ---- timing on the ctx stream (CUDA events) -------------------------------*/
+int fvm_timer_begin(fvm_ctx* ctx);
+int fvm_timer_end(fvm_ctx* ctx, float* out_ms); /* records, syncs, returns ms */
+
+/* ---- mesh + sparsity pattern -----------------------------------------------
+ * Replaces what the reference re-derives on every call from
+ * mesh.idx_hierarchy / ce_ratios / ei_dot_ei / node_coords / control_volumes
+ * and scipy's coo_matrix(...).tocsr() sort [README.md:49].  Built once per mesh
+ * on the device: radix sort of the half-edge (row, col) pairs -> CSR
+ * indptr/indices + the half-edge -> slot permutation, with the per-record
+ * geometry permuted into half-edge order. */
+typedef struct fvm_mesh_desc {
+  int32_t dim;          /* coordinate columns stored (2 or 3)                  */
+  int32_t n_vertices;   /* local vertices (owned rows + ghosts)                */
+  int32_t row_base;     /* first owned vertex id; rows = [row_base, +n_rows)   */
+  int32_t n_rows;       /* owned rows (== n_vertices on one GPU)               */
+  int64_t n_records;    /* columns of idx_hierarchy (edge contributions)       */
+  int32_t index_bytes;  /* 4 or 8: width of idx0/idx1 entries                  */
+  int32_t on_device;    /* 0: arrays below are host pointers; 1: device        */
+  const void* idx0;     /* [n_records] first endpoint  (idx_hierarchy[0].ravel) */
+  const void* idx1;     /* [n_records] second endpoint (idx_hierarchy[1].ravel) */
+  const double* ce_ratios;  /* [n_records]                                     */
+  const double* edge_len;   /* [n_records] sqrt(ei_dot_ei), may be NULL         */
+  const uint8_t* rec_mask;  /* [n_records] edge-term subdomain bits, may be NULL
+                               (records with mask 0 are left out of the pattern) */
+  const double* coords;     /* [n_vertices*dim] row-major                       */
+  const double* control_volumes; /* [n_vertices]                               */
+  int32_t tile_quantum; /* 0 = default; half-edges+slots per tile              */
+} fvm_mesh_desc;
+
+int fvm_mesh_create(fvm_ctx* ctx, const fvm_mesh_desc* desc, fvm_mesh** out);
+int fvm_mesh_destroy(fvm_mesh* mesh);
+/* nnz, number of half-edges kept, number of tiles, milliseconds spent in the
+ * on-device pattern build */
+int fvm_mesh_info(fvm_mesh* mesh, int64_t* nnz, int64_t* n_halfedges, int32_t* n_tiles,
+                  float* build_ms);
+/* CSR pattern to host: indptr[n_rows+1], indices[nnz] (local vertex ids) */
+int fvm_mesh_get_pattern(fvm_mesh* mesh, int32_t* indptr, int32_t* indices);
+/* device views of the same arrays (owned by the mesh) */
+int fvm_mesh_pattern_dev(fvm_mesh* mesh, const int32_t** indptr_dev, const int32_t** indices_dev);
+/* re-upload per-record geometry (same connectivity), permuted on the device */
+int fvm_mesh_update_geometry(fvm_mesh* mesh, const double* ce_ratios, const double* edge_len,
+                             const double* coords, const double* control_volumes, int on_device);
+
+/* ---- functor compilation (NVRTC -> sm_100a cubin) ---------------------------
+ * Replaces sympy.lambdify in the reference's discretize step: functor_src is
+ * the sympy.ccode-printed prelude (see pyfvm_b200/codegen.py); it is prepended
+ * to the built-in tile-kernel template. */
+int fvm_kernel_create(fvm_ctx* ctx, const char* functor_src, int mode, unsigned flags,
+                      int fmad, fvm_kernel** out);
+int fvm_kernel_destroy(fvm_kernel* k);
+/* registers/thread, static smem, and the SASS-visible name of the entry */
+int fvm_kernel_info(fvm_kernel* k, int* regs, int* static_smem, int* max_threads);
+/* the full source handed to NVRTC (template + prelude), for offline inspection */
+int fvm_kernel_source(const char* functor_src, char* out, size_t out_len, size_t* needed);
+
+/* ---- the hot path -------------------------------------------------------------
+ * One launch of the tile kernel over all rows of the mesh.
+ *   mode FVM_LINEAR   : data_dev[nnz], vec_dev[n_rows] (rhs) written
+ *   mode FVM_RESIDUAL : vec_dev[n_rows] (F) written; u_dev[n_vertices] read
+ *   mode FVM_JACOBIAN : data_dev[nnz] written;       u_dev[n_vertices] read
+ * vmask_dev / dirid_dev: per-vertex subdomain bits of the vertex terms and
+ * 1-based index of the winning Dirichlet term (0 = free row); may be NULL when
+ * the kernel was generated without them. */
+int fvm_assemble(fvm_mesh* mesh, fvm_kernel* k, const uint8_t* vmask_dev,
+                 const uint8_t* dirid_dev, const double* u_dev, double* data_dev,
+                 double* vec_dev);
+
+/* ---- small device helpers used around the path --------------------------------*/
+/* deterministic ||x||_2 (fixed-shape two-stage reduction) [README.md:121 newton] */
+int fvm_norm2(fvm_ctx* ctx, const double* x_dev, int64_t n, double* out);
+/* dst[i] = src[idx[i]]: halo pack for the row-partitioned multi-GPU path */
+int fvm_gather_f64(fvm_ctx* ctx, const double* src_dev, const int32_t* idx_dev, int64_t n,
+                   double* dst_dev);
+/* y += a*x (Newton update on the device) */
+int fvm_axpy(fvm_ctx* ctx, double a, const double* x_dev, double* y_dev, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,368 @@
+"""ctypes binding of ``libfvm_b200.so`` (C-ABI in ``include/fvm_b200.h``) and
+the per-mesh device state.
+
+There is no CPU fallback: if the CUDA library is missing or no B200 is
+visible, every entry point raises.
+"""
+import ctypes
+import hashlib
+import os
+import weakref
+from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int, c_int32, c_int64
+from ctypes import c_size_t, c_uint, c_uint8, c_void_p
+
+import numpy
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfvm_b200.so")
+
+KF_USES_EL = 1
+KF_EDGE_MASKED = 2
+
+
+class FvmError(RuntimeError):
+    pass
+
+
+class MeshDesc(ctypes.Structure):
+    # mirrors fvm_mesh_desc in include/fvm_b200.h
+    _fields_ = [
+        ("dim", c_int32),
+        ("n_vertices", c_int32),
+        ("row_base", c_int32),
+        ("n_rows", c_int32),
+        ("n_records", c_int64),
+        ("index_bytes", c_int32),
+        ("on_device", c_int32),
+        ("idx0", c_void_p),
+        ("idx1", c_void_p),
+        ("ce_ratios", c_void_p),
+        ("edge_len", c_void_p),
+        ("rec_mask", c_void_p),
+        ("coords", c_void_p),
+        ("control_volumes", c_void_p),
+        ("tile_quantum", c_int32),
+    ]
+
+
+# every symbol include/fvm_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "fvm_version": (c_int, []),
+    "fvm_last_error": (c_char_p, []),
+    "fvm_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "fvm_ctx_destroy": (c_int, [c_void_p]),
+    "fvm_ctx_sync": (c_int, [c_void_p]),
+    "fvm_ctx_info": (c_int, [c_void_p, c_char_p, c_size_t, POINTER(c_int), POINTER(c_size_t)]),
+    "fvm_dev_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
+    "fvm_dev_free": (c_int, [c_void_p, c_void_p]),
+    "fvm_dev_memset": (c_int, [c_void_p, c_void_p, c_int, c_size_t]),
+    "fvm_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "fvm_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "fvm_host_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
+    "fvm_host_free": (c_int, [c_void_p, c_void_p]),
+    "fvm_timer_begin": (c_int, [c_void_p]),
+    "fvm_timer_end": (c_int, [c_void_p, POINTER(c_float)]),
+    "fvm_mesh_create": (c_int, [c_void_p, POINTER(MeshDesc), POINTER(c_void_p)]),
+    "fvm_mesh_destroy": (c_int, [c_void_p]),
+    "fvm_mesh_info": (
+        c_int,
+        [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int32), POINTER(c_float)],
+    ),
+    "fvm_mesh_get_pattern": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "fvm_mesh_pattern_dev": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
+    "fvm_mesh_update_geometry": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "fvm_kernel_create": (c_int, [c_void_p, c_char_p, c_int, c_uint, c_int, POINTER(c_void_p)]),
+    "fvm_kernel_destroy": (c_int, [c_void_p]),
+    "fvm_kernel_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "fvm_kernel_source": (c_int, [c_char_p, c_char_p, c_size_t, POINTER(c_size_t)]),
+    "fvm_assemble": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "fvm_norm2": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double)]),
+    "fvm_gather_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "fvm_axpy": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_int64]),
+}
+
+_lib = None
+
+
+def load_library():
+    """Load the C-ABI library and bind every declared symbol (no GPU needed)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FvmError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or `make -C pyfvm_b200/csrc` (there is no CPU fallback)"
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    """Host pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+class DeviceBuffer:
+    """Device allocation owned by python; ``ptr`` is the raw device address."""
+
+    def __init__(self, eng, nbytes):
+        self.eng = eng
+        self.nbytes = int(nbytes)
+        p = c_void_p()
+        eng._ck(eng.lib.fvm_dev_alloc(eng.ctx, self.nbytes, byref(p)))
+        self.ptr = p.value
+        self._fin = weakref.finalize(self, eng.lib.fvm_dev_free, eng.ctx, c_void_p(self.ptr))
+
+    def free(self):
+        self._fin()
+
+    def upload(self, arr):
+        arr = numpy.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        self.eng._ck(self.eng.lib.fvm_h2d(self.eng.ctx, self.ptr, _ptr(arr), arr.nbytes))
+        return self
+
+    def download(self, out):
+        assert out.flags["C_CONTIGUOUS"] and out.nbytes <= self.nbytes
+        self.eng._ck(self.eng.lib.fvm_d2h(self.eng.ctx, _ptr(out), self.ptr, out.nbytes))
+        return out
+
+
+class Engine:
+    """One device context (= one CUDA stream on one GPU) plus the compiled
+    kernel cache.  ``Engine.get(device)`` returns the per-process singleton."""
+
+    _instances = {}
+
+    @classmethod
+    def get(cls, device=None):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        if device not in cls._instances:
+            cls._instances[device] = cls(device)
+        return cls._instances[device]
+
+    def __init__(self, device):
+        self.lib = load_library()
+        self.device = device
+        ctx = c_void_p()
+        rc = self.lib.fvm_ctx_create(device, byref(ctx))
+        if rc != 0:
+            raise FvmError(
+                "cannot create a B200 context (no CPU fallback): "
+                + self.lib.fvm_last_error().decode()
+            )
+        self.ctx = ctx
+        self._kernels = {}
+        self.launches = 0  # tile-kernel launches issued (bench's gpu_launches)
+        name = ctypes.create_string_buffer(256)
+        sm = c_int()
+        mem = c_size_t()
+        self._ck(self.lib.fvm_ctx_info(ctx, name, 256, byref(sm), byref(mem)))
+        self.name, self.sm_count, self.mem_bytes = name.value.decode(), sm.value, mem.value
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise FvmError(self.lib.fvm_last_error().decode())
+
+    # -- memory ---------------------------------------------------------------
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr):
+        arr = numpy.ascontiguousarray(arr)
+        return self.alloc(arr.nbytes).upload(arr)
+
+    def pinned_empty(self, shape, dtype):
+        """numpy array in page-locked host memory (fast, async-capable copies)."""
+        dtype = numpy.dtype(dtype)
+        n = int(numpy.prod(shape)) if not numpy.isscalar(shape) else int(shape)
+        nbytes = max(1, n * dtype.itemsize)
+        p = c_void_p()
+        self._ck(self.lib.fvm_host_alloc(self.ctx, nbytes, byref(p)))
+        raw = (ctypes.c_char * nbytes).from_address(p.value)
+        weakref.finalize(raw, self.lib.fvm_host_free, self.ctx, c_void_p(p.value))
+        return numpy.frombuffer(raw, dtype=dtype, count=n).reshape(shape)
+
+    def sync(self):
+        self._ck(self.lib.fvm_ctx_sync(self.ctx))
+
+    def timer_begin(self):
+        self._ck(self.lib.fvm_timer_begin(self.ctx))
+
+    def timer_end(self):
+        ms = c_float()
+        self._ck(self.lib.fvm_timer_end(self.ctx, byref(ms)))
+        return ms.value
+
+    # -- kernels ----------------------------------------------------------------
+    def kernel(self, functors, fmad=False):
+        """Compile (NVRTC, sm_100a) or fetch the cached tile kernel of a functor set."""
+        key = (hashlib.sha256(functors.source.encode()).hexdigest(), functors.mode, bool(fmad))
+        k = self._kernels.get(key)
+        if k is None:
+            flags = (KF_USES_EL if functors.uses_el else 0) | (
+                KF_EDGE_MASKED if functors.edge_masked else 0
+            )
+            h = c_void_p()
+            self._ck(
+                self.lib.fvm_kernel_create(
+                    self.ctx, functors.source.encode(), functors.mode, flags, int(fmad), byref(h)
+                )
+            )
+            k = Kernel(self, h, functors)
+            self._kernels[key] = k
+        return k
+
+    def kernel_source(self, functors):
+        need = c_size_t()
+        self.lib.fvm_kernel_source(functors.source.encode(), None, 0, byref(need))
+        buf = ctypes.create_string_buffer(need.value)
+        self.lib.fvm_kernel_source(functors.source.encode(), buf, need.value, byref(need))
+        return buf.value.decode()
+
+    def norm2(self, x_dev, n):
+        out = c_double()
+        self._ck(self.lib.fvm_norm2(self.ctx, x_dev, n, byref(out)))
+        return out.value
+
+
+class Kernel:
+    def __init__(self, eng, handle, functors):
+        self.eng, self.handle, self.functors = eng, handle, functors
+
+    def info(self):
+        r, s, t = c_int(), c_int(), c_int()
+        self.eng._ck(self.eng.lib.fvm_kernel_info(self.handle, byref(r), byref(s), byref(t)))
+        return {"regs": r.value, "static_smem": s.value, "max_threads": t.value}
+
+
+def _mesh_arrays(mesh):
+    """Read the meshplex attribute contract once."""
+    idx = numpy.asarray(mesh.idx_hierarchy)
+    coords = numpy.asarray(
+        mesh.node_coords if hasattr(mesh, "node_coords") else mesh.points, dtype=numpy.float64
+    )
+    dim = coords.shape[1]
+    if dim == 3 and not numpy.any(coords[:, 2]):
+        dim = 2  # planar mesh carried with a zero third column
+    return idx, coords, dim
+
+
+class DeviceMesh:
+    """Device mirror of one mesh (+ optional per-record subdomain bits): the
+    CSR pattern, the half-edge streams and the vertex arrays.  Built once and
+    cached per mesh object, like meshplex caches its own derived arrays."""
+
+    def __init__(self, eng, mesh, rec_mask=None, need_el=True, row_range=None, tile_quantum=0):
+        self.eng = eng
+        idx, coords, dim = _mesh_arrays(mesh)
+        self.dim = dim
+        self.n = coords.shape[0]
+        idx0 = numpy.ascontiguousarray(idx[0].reshape(-1))
+        idx1 = numpy.ascontiguousarray(idx[1].reshape(-1))
+        if idx0.dtype not in (numpy.int32, numpy.int64):
+            idx0, idx1 = idx0.astype(numpy.int64), idx1.astype(numpy.int64)
+        ce = numpy.ascontiguousarray(numpy.asarray(mesh.ce_ratios, dtype=numpy.float64).reshape(-1))
+        el = None
+        if need_el:
+            el = numpy.sqrt(numpy.asarray(mesh.ei_dot_ei, dtype=numpy.float64)).reshape(-1)
+            el = numpy.ascontiguousarray(el)
+        xy = numpy.ascontiguousarray(coords[:, :dim])
+        cv = numpy.ascontiguousarray(numpy.asarray(mesh.control_volumes, dtype=numpy.float64))
+        if rec_mask is not None:
+            rec_mask = numpy.ascontiguousarray(rec_mask, dtype=numpy.uint8)
+            assert rec_mask.shape == idx0.shape
+        self.R = idx0.shape[0]
+        row_base, n_rows = (0, self.n) if row_range is None else row_range
+        self.row_base, self.n_rows = row_base, n_rows
+        d = MeshDesc(
+            dim=dim,
+            n_vertices=self.n,
+            row_base=row_base,
+            n_rows=n_rows,
+            n_records=self.R,
+            index_bytes=idx0.dtype.itemsize,
+            on_device=0,
+            idx0=_ptr(idx0),
+            idx1=_ptr(idx1),
+            ce_ratios=_ptr(ce),
+            edge_len=_ptr(el),
+            rec_mask=_ptr(rec_mask),
+            coords=_ptr(xy),
+            control_volumes=_ptr(cv),
+            tile_quantum=tile_quantum,
+        )
+        h = c_void_p()
+        eng._ck(eng.lib.fvm_mesh_create(eng.ctx, byref(d), byref(h)))
+        self.handle = h
+        self._fin = weakref.finalize(self, eng.lib.fvm_mesh_destroy, h)
+        self.has_el = el is not None
+        nnz, nhe, ntiles, ms = c_int64(), c_int64(), c_int32(), c_float()
+        eng._ck(eng.lib.fvm_mesh_info(h, byref(nnz), byref(nhe), byref(ntiles), byref(ms)))
+        self.nnz, self.n_halfedges, self.n_tiles, self.build_ms = (
+            nnz.value,
+            nhe.value,
+            ntiles.value,
+            ms.value,
+        )
+        self._pattern = None
+
+    def pattern(self):
+        """Host copy of ``(indptr, indices)`` (int32), fetched once."""
+        if self._pattern is None:
+            indptr = numpy.empty(self.n_rows + 1, dtype=numpy.int32)
+            indices = numpy.empty(self.nnz, dtype=numpy.int32)
+            self.eng._ck(
+                self.eng.lib.fvm_mesh_get_pattern(self.handle, _ptr(indptr), _ptr(indices))
+            )
+            self._pattern = (indptr, indices)
+        return self._pattern
+
+    def update_geometry(self, ce=None, el=None, coords=None, cv=None):
+        """Re-upload per-record / per-vertex geometry of the same connectivity
+        (host arrays; the device permutes records into half-edge order)."""
+        arrs = [None if a is None else numpy.ascontiguousarray(a, dtype=numpy.float64)
+                for a in (ce, el, coords, cv)]
+        self.eng._ck(
+            self.eng.lib.fvm_mesh_update_geometry(self.handle, *[_ptr(a) for a in arrs], 0)
+        )
+
+    def launch(self, kernel, vmask=None, dirid=None, u=None, data=None, vec=None):
+        """One tile-kernel launch; all arguments are device addresses (int) or None."""
+        self.eng._ck(
+            self.eng.lib.fvm_assemble(self.handle, kernel.handle, vmask, dirid, u, data, vec)
+        )
+        self.eng.launches += 1
+
+
+_mesh_cache = {}
+
+
+def device_mesh(eng, mesh, rec_mask=None, need_el=False, row_range=None):
+    """Cached :class:`DeviceMesh` of ``mesh`` (key: mesh identity, subdomain bits,
+    owned row range)."""
+    mkey = None if rec_mask is None else hashlib.sha256(rec_mask.tobytes()).hexdigest()
+    key = (id(mesh), eng.device, mkey, row_range)
+    dm = _mesh_cache.get(key)
+    if dm is not None and need_el and not dm.has_el:
+        dm = None  # rebuild with the edge-length stream
+    if dm is None:
+        dm = DeviceMesh(eng, mesh, rec_mask=rec_mask, need_el=need_el, row_range=row_range)
+        _mesh_cache[key] = dm
+        try:
+            weakref.finalize(mesh, _mesh_cache.pop, key, None)
+        except TypeError:
+            pass  # mesh object not weak-referenceable: cache lives with the process
+    return dm

@@ -1,0 +1,208 @@
+"""Numeric half of the drop-in: what ``discretize_linear`` / ``discretize``
+hand back, backed by the device engine.
+
+Reference surface reproduced here:
+* ``pyfvm.discretize_linear(problem, mesh) -> (matrix, rhs)``        [README:49]
+* ``pyfvm.discretize(problem, mesh) -> (f, jacobian)``               [README:110]
+* ``f.eval(u) -> ndarray``                                           [README:121, 136]
+* ``jacobian.get_linear_operator(u0) -> scipy CSR``                  [README:116]
+"""
+import numpy
+from scipy import sparse
+
+from . import codegen, lowering
+from .engine import Engine, device_mesh, _mesh_arrays
+
+_KEEP_BIT = 0x80  # record is covered by at least one edge term without subdomain
+
+
+def _edge_bits(mesh, lowered):
+    """Per-record subdomain bits of the edge terms (None: all terms everywhere)."""
+    bits, rec_mask, nbit = [], None, 0
+    if all(t.subdomain is None for t in lowered.edge):
+        return [None] * len(lowered.edge), None
+    idx = numpy.asarray(mesh.idx_hierarchy)
+    shape = idx.shape[1:]
+    rec_mask = numpy.zeros(shape, dtype=numpy.uint8)
+    for t in lowered.edge:
+        if t.subdomain is None:
+            bits.append(None)
+            rec_mask |= _KEEP_BIT
+        else:
+            if nbit >= 7:
+                raise NotImplementedError("more than 7 subdomain-restricted dS terms")
+            cell_mask = numpy.asarray(mesh.get_cell_mask(t.subdomain), dtype=bool)
+            rec_mask[..., cell_mask] |= 1 << nbit
+            bits.append(nbit)
+            nbit += 1
+    return bits, numpy.ascontiguousarray(rec_mask.reshape(-1))
+
+
+def _vertex_bits(mesh, lowered, n):
+    bits, vmask, nbit = [], None, 0
+    for t in lowered.vertex:
+        if t.subdomain is None:
+            bits.append(None)
+            continue
+        if vmask is None:
+            vmask = numpy.zeros(n, dtype=numpy.uint8)
+        if nbit >= 8:
+            raise NotImplementedError("more than 8 subdomain-restricted dV terms")
+        vmask[mesh.get_vertex_mask(t.subdomain)] |= 1 << nbit
+        bits.append(nbit)
+        nbit += 1
+    return bits, vmask
+
+
+def _dirichlet_ids(mesh, lowered, n):
+    """1-based index of the last Dirichlet term covering each vertex (later
+    conditions overwrite earlier ones, as in the reference's loop)."""
+    if not lowered.dirichlet:
+        return None
+    if len(lowered.dirichlet) > 255:
+        raise NotImplementedError("more than 255 Dirichlet conditions")
+    ids = numpy.zeros(n, dtype=numpy.uint8)
+    for k, t in enumerate(lowered.dirichlet):
+        ids[mesh.get_vertex_mask(t.subdomain)] = k + 1
+    return ids
+
+
+class _DeviceProblem:
+    """State shared by the linear problem, the residual and the Jacobian of one
+    (problem, mesh) pair: device mesh, vertex masks, compiled kernels, buffers."""
+
+    def __init__(self, obj, mesh, kind, device=None, fmad=False, row_range=None):
+        self.eng = eng = Engine.get(device)
+        _, coords, dim = _mesh_arrays(mesh)
+        self.n = n = coords.shape[0]
+        lower = lowering.lower_linear if kind == "linear" else lowering.lower_nonlinear
+        self.lowered = lowered = lower(obj, dim)
+        ebits, rec_mask = _edge_bits(mesh, lowered)
+        vbits, vmask = _vertex_bits(mesh, lowered, n)
+        dirid = _dirichlet_ids(mesh, lowered, n)
+        modes = (
+            [codegen.MODE_LINEAR]
+            if kind == "linear"
+            else [codegen.MODE_RESIDUAL, codegen.MODE_JACOBIAN]
+        )
+        self.functors = {m: codegen.generate(lowered, m, ebits, vbits) for m in modes}
+        need_el = any(f.uses_el for f in self.functors.values())
+        # row_range = (first owned vertex, owned rows): row-partitioned multi-GPU runs
+        self.dmesh = device_mesh(
+            eng, mesh, rec_mask=rec_mask, need_el=need_el, row_range=row_range
+        )
+        self.n_rows = self.dmesh.n_rows
+        self.kernels = {m: eng.kernel(f, fmad=fmad) for m, f in self.functors.items()}
+        self.vmask = eng.to_device(vmask) if vmask is not None else None
+        self.dirid = eng.to_device(dirid) if dirid is not None else None
+        self.nnz = self.dmesh.nnz
+        self.data = eng.alloc(8 * self.nnz)
+        self.vec = eng.alloc(8 * n)
+        self.u = eng.alloc(8 * n)
+
+    def _p(self, buf):
+        return None if buf is None else buf.ptr
+
+    def launch(self, mode, u_ptr=None, data_ptr=None, vec_ptr=None):
+        self.dmesh.launch(
+            self.kernels[mode],
+            vmask=self._p(self.vmask),
+            dirid=self._p(self.dirid),
+            u=u_ptr,
+            data=data_ptr,
+            vec=vec_ptr,
+        )
+
+    def csr(self, data_host):
+        """scipy CSR on the cached pattern (sorted, duplicate-free, int32)."""
+        indptr, indices = self.dmesh.pattern()
+        m = sparse.csr_matrix(
+            (data_host, indices, indptr), shape=(self.n_rows, self.n), copy=False
+        )
+        m.has_sorted_indices = True
+        m.has_canonical_format = True
+        return m
+
+    def upload_u(self, u):
+        u = numpy.ascontiguousarray(u, dtype=numpy.float64)
+        assert u.shape == (self.n,), "u must have one value per vertex"
+        self.u.upload(u)
+        return self.u.ptr
+
+
+class LinearProblem(_DeviceProblem):
+    """``discretize_linear``'s numeric half: one tile-kernel launch writes the CSR
+    values and the right-hand side (Dirichlet rows replaced in the same pass)."""
+
+    def __init__(self, obj, mesh, **kw):
+        super().__init__(obj, mesh, "linear", **kw)
+
+    def update_geometry(self, **kw):
+        self.dmesh.update_geometry(**kw)
+
+    def assemble_device(self):
+        """Launch only; results stay in ``self.data`` / ``self.vec`` on the device."""
+        self.launch(codegen.MODE_LINEAR, data_ptr=self.data.ptr, vec_ptr=self.vec.ptr)
+
+    def assemble(self, pinned=False):
+        self.assemble_device()
+        if pinned:
+            data = self.eng.pinned_empty(self.nnz, numpy.float64)
+            rhs = self.eng.pinned_empty(self.n_rows, numpy.float64)
+        else:
+            data = numpy.empty(self.nnz)
+            rhs = numpy.empty(self.n_rows)
+        self.data.download(data)
+        self.vec.download(rhs)
+        return self.csr(data), rhs
+
+
+class FvmProblem:
+    """The residual ``f`` returned by ``discretize`` [README:110]."""
+
+    def __init__(self, state):
+        self._s = state
+
+    def eval(self, u):
+        """``F(u)`` as a host array [README:121, 136]; ``u`` is a host array."""
+        s = self._s
+        self.eval_device(s.upload_u(u))
+        out = numpy.empty(s.n_rows)
+        s.vec.download(out)
+        return out
+
+    def eval_device(self, u_ptr, out_ptr=None):
+        """Device-resident fast path: ``u_ptr`` / ``out_ptr`` are device addresses."""
+        s = self._s
+        s.launch(codegen.MODE_RESIDUAL, u_ptr=u_ptr, vec_ptr=out_ptr or s.vec.ptr)
+
+
+class Jacobian:
+    """The Jacobian returned by ``discretize``; values are refreshed in place on
+    the fixed sparsity pattern (no COO rebuild, no sort)."""
+
+    def __init__(self, state):
+        self._s = state
+
+    def get_linear_operator(self, u):
+        """CSR Jacobian at ``u`` usable by ``spsolve`` [README:116-117]."""
+        s = self._s
+        self.values_device(s.upload_u(u))
+        data = numpy.empty(s.nnz)
+        s.data.download(data)
+        return s.csr(data)
+
+    def values_device(self, u_ptr, out_ptr=None):
+        s = self._s
+        s.launch(codegen.MODE_JACOBIAN, u_ptr=u_ptr, data_ptr=out_ptr or s.data.ptr)
+
+
+def discretize_linear(obj, mesh, device=None, fmad=False):
+    """``pyfvm.discretize_linear(problem, mesh) -> (matrix, rhs)`` [README:49]."""
+    return LinearProblem(obj, mesh, device=device, fmad=fmad).assemble()
+
+
+def discretize(obj, mesh, device=None, fmad=False):
+    """``pyfvm.discretize(problem, mesh) -> (f, jacobian)`` [README:110]."""
+    state = _DeviceProblem(obj, mesh, "nonlinear", device=device, fmad=fmad)
+    return FvmProblem(state), Jacobian(state)
