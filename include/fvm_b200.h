@@ -39,9 +39,15 @@ typedef struct fvm_kernel fvm_kernel;
 #define FVM_RESIDUAL 1 /* f.eval(u)                             [README.md:121] */
 #define FVM_JACOBIAN 2 /* jacobian.get_linear_operator(u0)      [README.md:116] */
 
-/* fvm_kernel_create flags */
-#define FVM_KF_USES_EL 1u     /* edge functor reads edge_length              */
-#define FVM_KF_EDGE_MASKED 2u /* edge terms restricted to cell subdomains    */
+/* fvm_kernel_create flags: what the functor set reads (must equal the
+ * FVM_FLAGS the generated prelude defines) */
+#define FVM_KF_EDGE_EL 1u    /* edge functor reads edge_length               */
+#define FVM_KF_EDGE_MASK 2u  /* edge terms restricted to cell subdomains     */
+#define FVM_KF_X 4u          /* some functor reads vertex coordinates        */
+#define FVM_KF_U 8u          /* some functor reads the state u               */
+#define FVM_KF_CV 16u        /* vertex functor reads control volumes         */
+#define FVM_KF_VMASK 32u     /* vertex terms restricted to vertex subdomains */
+#define FVM_KF_DIR 64u       /* Dirichlet conditions present                 */
 
 int fvm_version(void);
 const char* fvm_last_error(void);
@@ -110,11 +116,21 @@ int fvm_mesh_update_geometry(fvm_mesh* mesh, const double* ce_ratios, const doub
  * Replaces sympy.lambdify in the reference's discretize step: functor_src is
  * the sympy.ccode-printed prelude (see pyfvm_b200/codegen.py); it is prepended
  * to the built-in tile-kernel template. */
-int fvm_kernel_create(fvm_ctx* ctx, const char* functor_src, int mode, unsigned flags,
-                      int fmad, fvm_kernel** out);
+typedef struct fvm_kernel_opts {
+  int32_t mode;           /* FVM_LINEAR / FVM_RESIDUAL / FVM_JACOBIAN               */
+  uint32_t flags;         /* FVM_KF_* bits; must equal the prelude's FVM_FLAGS      */
+  int32_t fmad;           /* 0: --fmad=false (numpy-like rounding), 1: allow FMA    */
+  int32_t consumer_warps; /* math warps per CTA; must equal FVM_CONSUMER_WARPS      */
+  int32_t stages;         /* shared-memory ring depth; must equal FVM_STAGES        */
+  int32_t ctas_per_sm;    /* persistent CTAs per SM, 0 = as many as fit             */
+} fvm_kernel_opts;
+int fvm_kernel_create(fvm_ctx* ctx, const char* functor_src, const fvm_kernel_opts* opts,
+                      fvm_kernel** out);
 int fvm_kernel_destroy(fvm_kernel* k);
-/* registers/thread, static smem, and the SASS-visible name of the entry */
+/* registers/thread, static smem, max threads/block of the compiled entry */
 int fvm_kernel_info(fvm_kernel* k, int* regs, int* static_smem, int* max_threads);
+/* launch shape the kernel would use on this mesh: grid, block, dynamic smem bytes */
+int fvm_kernel_launch_shape(fvm_kernel* k, fvm_mesh* mesh, int* grid, int* block, int* smem);
 /* the full source handed to NVRTC (template + prelude), for offline inspection */
 int fvm_kernel_source(const char* functor_src, char* out, size_t out_len, size_t* needed);
 

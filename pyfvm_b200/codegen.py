@@ -5,6 +5,7 @@ in the reference's discretize step; SURVEY §2 "back end replaced", App. A.6).
 three functors ``fvm_edge`` / ``fvm_vertex`` / ``fvm_dirichlet``) that is
 prepended to ``csrc/fvm_tile_kernel.cuh`` and compiled by NVRTC for sm_100a.
 """
+import os
 from dataclasses import dataclass
 
 import sympy
@@ -13,7 +14,20 @@ from sympy.printing.c import C99CodePrinter
 from . import lowering as lo
 
 MODE_LINEAR, MODE_RESIDUAL, MODE_JACOBIAN = 0, 1, 2
-THREADS = 256
+
+# FVM_F_* bits of csrc/fvm_tile_args.h (= FVM_KF_* of include/fvm_b200.h)
+F_EDGE_EL, F_EDGE_MASK, F_X, F_U, F_CV, F_VMASK, F_DIR = 1, 2, 4, 8, 16, 32, 64
+
+
+def tuning():
+    """Launch-shape knobs of the tile kernel (env overrides are for experiments)."""
+    return {
+        "consumer_warps": int(os.environ.get("FVM_CONSUMER_WARPS", "8")),
+        "stages": int(os.environ.get("FVM_STAGES", "2")),
+        "ctas_per_sm": int(os.environ.get("FVM_CTAS_PER_SM", "0")),
+        # fold the ce_ratios of a slot first and evaluate ce*g(slot) once
+        "factor_ce": int(os.environ.get("FVM_FACTOR_CE", "1")),
+    }
 
 # functor outputs per mode: (edge D, O, C), (vertex L, C), (dirichlet coeff, val)
 _EDGE_KEYS = {
@@ -82,6 +96,16 @@ def _emit_masked(lines, bit, targets, exprs):
     lines.extend(block)
 
 
+def _is_linear_in_ce(e):
+    """``e == edge_ce_ratio * g`` with ``g`` free of ``edge_ce_ratio``."""
+    e = sympy.sympify(e)
+    if e == 0:
+        return True
+    if e.subs(lo.CE, 0) != 0:
+        return False
+    return lo.CE not in sympy.diff(e, lo.CE).free_symbols
+
+
 def _uses(exprs, symbols):
     fs = set()
     for e in exprs:
@@ -93,14 +117,20 @@ def _uses(exprs, symbols):
 class Functors:
     source: str  # prelude to prepend to the tile-kernel template
     mode: int
+    flags: int  # FVM_F_* bits: which streams the kernel stages / the host must supply
+    consumer_warps: int
+    stages: int
+    ctas_per_sm: int
+    factored: bool
     uses_el: bool
+    uses_x: bool
     edge_masked: bool
     vert_masked: bool
     has_dirichlet: bool
     needs_u: bool
 
 
-def generate(lowered, mode, edge_bits, vert_bits, fmad=False):
+def generate(lowered, mode, edge_bits, vert_bits, tune=None):
     """Print the functor prelude for ``mode``.
 
     ``edge_bits[i]`` / ``vert_bits[i]`` is the subdomain mask bit of edge /
@@ -113,20 +143,39 @@ def generate(lowered, mode, edge_bits, vert_bits, fmad=False):
     flat_e = [e for ex in edge_exprs for e in ex]
     flat_v = [e for ex in vert_exprs + dir_exprs for e in ex]
     xv = lo.X0 + lo.X1
+    tune = tune or tuning()
+    edge_x, vert_x = _uses(flat_e, xv), _uses(flat_v, lo.XV)
+    edge_u, vert_u = _uses(flat_e, [lo.UK0, lo.UK1]), _uses(flat_v, [lo.UK0])
+    flags = 0
+    flags |= F_EDGE_EL if _uses(flat_e, [lo.EL]) else 0
+    flags |= F_EDGE_MASK if any(b is not None for b in edge_bits) else 0
+    flags |= F_X if (edge_x or vert_x) else 0
+    flags |= F_U if (edge_u or vert_u) else 0
+    flags |= F_CV if _uses(flat_v, [lo.CV]) else 0
+    flags |= F_VMASK if any(b is not None for b in vert_bits) else 0
+    flags |= F_DIR if lowered.dirichlet else 0
+    # Every dS integrand is multiplied by edge_ce_ratio (App. A.2), so the edge
+    # outputs are ce * g(x0, x1, u0, u1).  When nothing else varies per half-edge
+    # (no edge_length, no subdomain bits) the kernel sums the ce_ratios of a slot
+    # and evaluates the functor once with that sum.
+    factored = bool(
+        tune.get("factor_ce", 1)
+        and flat_e
+        and not (flags & (F_EDGE_EL | F_EDGE_MASK))
+        and all(_is_linear_in_ce(e) for e in flat_e)
+    )
     defs = {
         "FVM_MODE": mode,
         "FVM_DIM": lowered.dim,
-        "FVM_THREADS": THREADS,
-        "FVM_EDGE_USES_X": int(_uses(flat_e, xv)),
-        "FVM_EDGE_USES_EL": int(_uses(flat_e, [lo.EL])),
-        "FVM_EDGE_USES_U": int(_uses(flat_e, [lo.UK0, lo.UK1])),
-        "FVM_EDGE_MASKED": int(any(b is not None for b in edge_bits)),
-        "FVM_VERT_USES_X": int(_uses(flat_v, lo.XV)),
-        "FVM_VERT_USES_U": int(_uses(flat_v, [lo.UK0])),
-        "FVM_VERT_USES_CV": int(_uses(flat_v, [lo.CV])),
-        "FVM_VERT_MASKED": int(any(b is not None for b in vert_bits)),
+        "FVM_FLAGS": f"{flags}u",
+        "FVM_CONSUMER_WARPS": tune["consumer_warps"],
+        "FVM_STAGES": tune["stages"],
+        "FVM_EDGE_FACTORED": int(factored),
+        "FVM_EDGE_USES_X": int(edge_x),
+        "FVM_EDGE_USES_U": int(edge_u),
+        "FVM_VERT_USES_X": int(vert_x),
+        "FVM_VERT_USES_U": int(vert_u),
         "FVM_HAS_VERTEX": int(bool(lowered.vertex)),
-        "FVM_HAS_DIRICHLET": int(bool(lowered.dirichlet)),
     }
     bad = set()
     for e in flat_e + flat_v:
@@ -175,9 +224,15 @@ def generate(lowered, mode, edge_bits, vert_bits, fmad=False):
     return Functors(
         source="\n".join(L),
         mode=mode,
-        uses_el=bool(defs["FVM_EDGE_USES_EL"]),
-        edge_masked=bool(defs["FVM_EDGE_MASKED"]),
-        vert_masked=bool(defs["FVM_VERT_MASKED"]),
-        has_dirichlet=bool(defs["FVM_HAS_DIRICHLET"]),
-        needs_u=bool(defs["FVM_EDGE_USES_U"] or defs["FVM_VERT_USES_U"]),
+        flags=flags,
+        consumer_warps=tune["consumer_warps"],
+        stages=tune["stages"],
+        ctas_per_sm=tune["ctas_per_sm"],
+        factored=factored,
+        uses_el=bool(flags & F_EDGE_EL),
+        uses_x=bool(flags & F_X),
+        edge_masked=bool(flags & F_EDGE_MASK),
+        vert_masked=bool(flags & F_VMASK),
+        has_dirichlet=bool(flags & F_DIR),
+        needs_u=bool(flags & F_U),
     )

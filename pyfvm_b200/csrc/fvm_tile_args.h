@@ -3,13 +3,20 @@
 #ifndef FVM_TILE_ARGS_H
 #define FVM_TILE_ARGS_H
 
-// A "tile" is a run of consecutive matrix rows [tile_row[t], tile_row[t+1])
-// whose half-edges and CSR slots are contiguous in HBM:
-//   half-edges [heptr[r0], heptr[r1])   -> he_ce / he_el / he_mask streams
-//   slots      [indptr[r0], indptr[r1]) -> colidx / slot_off / data
+// A "tile" is a run of consecutive matrix rows [r0, r0+nr) whose half-edges
+// and CSR slots are contiguous in HBM:
+//   half-edges [h0, h0+nhe) -> he_ce / he_el / he_mask streams
+//   slots      [s0, s0+nsl) -> colidx / slot_off / data
+//   vertices   [row_base+r0, +nr) -> coords / cv / u / dir_id / vmask slices
+struct FvmTileDesc {  // 32 bytes, one per tile
+  long long h0;
+  int r0, nr;
+  int s0, nsl;
+  int nhe, pad;
+};
+
 struct FvmTileArgs {
-  const int* tile_row;             // [ntiles+1] first row of every tile
-  const long long* heptr;          // [nrows+1] first half-edge of every row
+  const FvmTileDesc* tiles;        // [ntiles]
   const int* indptr;               // [nrows+1] CSR row pointer
   const int* colidx;               // [nnz] column (local vertex id) of every slot
   const unsigned short* slot_off;  // [nnz] first half-edge of the slot, relative to its tile
@@ -34,10 +41,24 @@ struct FvmTileArgs {
 #define FVM_MODE_RESIDUAL 1  // F(u) (f.eval)
 #define FVM_MODE_JACOBIAN 2  // matrix values at u (jacobian.get_linear_operator)
 
+// What a functor set reads; decides which streams are staged in shared memory.
+#define FVM_F_EDGE_EL 1u    // edge functor reads edge_length
+#define FVM_F_EDGE_MASK 2u  // edge terms carry cell-subdomain bits
+#define FVM_F_X 4u          // any functor reads vertex coordinates
+#define FVM_F_U 8u          // any functor reads the state u
+#define FVM_F_CV 16u        // vertex functor reads control volumes
+#define FVM_F_VMASK 32u     // vertex terms carry vertex-subdomain bits
+#define FVM_F_DIR 64u       // Dirichlet conditions present
 
-// Dynamic shared-memory carve-up of one CTA, identical on host and device.
+// Dynamic shared-memory carve-up of one CTA, identical on host and device:
+//   [full/empty mbarriers][stage 0][stage 1]...[scratch: pd pc srow dpos]
+// The stream offsets (desc .. vmask) are relative to the start of a stage.
+// Every staged stream gets 16 spare bytes: its bulk copy starts at the 16B
+// boundary below the first element and is rounded up to 16B.
 struct FvmSmemLayout {
-  unsigned bar, ce, el, mask, pd, pc, srow, dpos, total;
+  unsigned bar, stage0, stage_bytes;
+  unsigned desc, ce, el, mask, col, off, rowptr, cv, xy, u, dir, vmask;  // within a stage
+  unsigned pd, pc, srow, dpos, total;
 };
 
 #ifdef __CUDACC__
@@ -48,19 +69,31 @@ struct FvmSmemLayout {
 
 FVM_HD inline unsigned fvm_round16(unsigned x) { return (x + 15u) & ~15u; }
 
-FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_rows,
-                                            int uses_el, int masked) {
+FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_rows, int dim,
+                                            unsigned flags, int mode, int stages) {
   FvmSmemLayout L;
-  unsigned o = 0;
-  L.bar = o;  o += 16;
-  // +2 doubles: the bulk copy starts at an even half-edge and ends 16B-rounded
-  L.ce = o;   o += fvm_round16((unsigned)(max_he + 2) * 8u);
-  L.el = o;   o += uses_el ? fvm_round16((unsigned)(max_he + 2) * 8u) : 0u;
-  L.mask = o; o += masked ? fvm_round16((unsigned)max_he + 32u) : 0u;
-  L.pd = o;   o += fvm_round16((unsigned)max_slots * 8u);
-  L.pc = o;   o += fvm_round16((unsigned)max_slots * 8u);
-  L.srow = o; o += fvm_round16((unsigned)max_slots * 2u);
-  L.dpos = o; o += fvm_round16((unsigned)max_rows * 2u);
+  const unsigned he = (unsigned)max_he, sl = (unsigned)max_slots, nr = (unsigned)max_rows;
+  unsigned o = 0;  // within a stage
+  L.desc = o;   o += 32;
+  L.ce = o;     o += fvm_round16(he * 8u) + 16u;
+  L.el = o;     o += (flags & FVM_F_EDGE_EL) ? fvm_round16(he * 8u) + 16u : 0u;
+  L.mask = o;   o += (flags & FVM_F_EDGE_MASK) ? fvm_round16(he) + 16u : 0u;
+  L.col = o;    o += fvm_round16(sl * 4u) + 16u;
+  L.off = o;    o += fvm_round16(sl * 2u) + 16u;
+  L.rowptr = o; o += fvm_round16((nr + 1u) * 4u) + 16u;
+  L.cv = o;     o += (flags & FVM_F_CV) ? fvm_round16(nr * 8u) + 16u : 0u;
+  L.xy = o;     o += (flags & FVM_F_X) ? fvm_round16(nr * 8u * (unsigned)dim) + 16u : 0u;
+  L.u = o;      o += (flags & FVM_F_U) ? fvm_round16(nr * 8u) + 16u : 0u;
+  L.dir = o;    o += (flags & FVM_F_DIR) ? fvm_round16(nr) + 16u : 0u;
+  L.vmask = o;  o += (flags & FVM_F_VMASK) ? fvm_round16(nr) + 16u : 0u;
+  L.stage_bytes = o;
+  L.bar = 0;
+  L.stage0 = fvm_round16(16u * (unsigned)stages);  // 2 x 8B mbarriers per stage
+  o = L.stage0 + L.stage_bytes * (unsigned)stages;
+  L.pd = o;     o += (mode != FVM_MODE_RESIDUAL) ? fvm_round16(sl * 8u) : 0u;
+  L.pc = o;     o += (mode != FVM_MODE_JACOBIAN) ? fvm_round16(sl * 8u) : 0u;
+  L.srow = o;   o += fvm_round16(sl * 2u);
+  L.dpos = o;   o += fvm_round16(nr * 2u);
   L.total = o;
   return L;
 }

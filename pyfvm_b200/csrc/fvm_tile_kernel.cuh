@@ -6,9 +6,8 @@
 //   FVM_MODE_JACOBIAN : jacobian.get_linear_operator(u0) values         [README:116]
 //
 // It is compiled at run time by NVRTC after a generated prelude that defines
-//   FVM_MODE, FVM_DIM, FVM_THREADS,
-//   FVM_EDGE_USES_X / _EL / _U, FVM_VERT_USES_X / _U / _CV, FVM_EDGE_MASKED,
-//   FVM_VERT_MASKED, FVM_HAS_DIRICHLET, FVM_HAS_VERTEX
+//   FVM_MODE, FVM_DIM, FVM_FLAGS (FVM_F_* bits), FVM_CONSUMER_WARPS, FVM_STAGES,
+//   FVM_EDGE_USES_X / _U, FVM_VERT_USES_X / _U, FVM_HAS_VERTEX, FVM_EDGE_FACTORED
 // and the three sympy-printed device functors
 //   fvm_edge(uk0, uk1, x0_0..2, x1_0..2, edge_ce_ratio, edge_length, mask, &D, &O, &C)
 //   fvm_vertex(uk0, control_volume, x_0..2, mask, &L, &C)
@@ -16,24 +15,44 @@
 // (edge functor outputs per half-edge (row, col): D -> slot (row,row),
 //  O -> slot (row,col), C -> rhs/residual of row).
 //
-// Data movement per CTA (= one tile of consecutive rows):
-//   1. one elected thread issues TMA bulk copies (cp.async.bulk, UBLKCP) of the
-//      tile's contiguous ce_ratio / edge_length / mask streams into shared
-//      memory, completion tracked by an mbarrier;
-//   2. meanwhile all threads paint slot -> row into shared memory;
-//   3. slot-parallel phase: thread s folds the contributions of CSR slot s from
-//      shared memory in half-edge order (deterministic, atomic-free), gathers
-//      x/u of its column once, and stores data[s] coalesced;
-//   4. row-parallel phase: thread r folds the per-slot partials of its row into
-//      the diagonal slot and rhs/F, adds the vertex term and applies the
-//      Dirichlet row replacement in the same pass.
+// Persistent, warp-specialised CTAs (grid = resident CTAs of the whole GPU);
+// CTA b walks tiles b, b+grid, ... through a ring of FVM_STAGES shared-memory
+// stages guarded by full/empty mbarriers:
+//   producer warp  : reads the 32-byte tile descriptor and issues TMA bulk copies
+//                    (cp.async.bulk, SASS UBLKCP) of every contiguous stream the
+//                    tile needs -- ce_ratio / edge_length / mask per half-edge,
+//                    column + offset per slot, row pointer / coords / cv / u /
+//                    Dirichlet id per row -- one or more tiles ahead of the math;
+//   consumer warps : (2) paint slot -> row, (3) slot-parallel: thread s folds the
+//                    contributions of CSR slot s from shared memory in half-edge
+//                    order (deterministic, atomic-free), gathering x/u only for
+//                    columns outside the tile, and stores data[s] coalesced,
+//                    (4) row-parallel: thread r folds the per-slot partials of its
+//                    row into the diagonal slot and rhs/F, adds the vertex term
+//                    and applies the Dirichlet row replacement in the same pass.
 // The fold order of a slot/row depends only on the row's own half-edge order,
-// never on tile boundaries, so a row-partitioned multi-GPU run is bit-identical
-// to the single-GPU run.
+// never on tile boundaries or the grid size, so a row-partitioned multi-GPU run
+// is bit-identical to the single-GPU run.
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
 #endif
+
+#define FVM_EDGE_USES_EL ((FVM_FLAGS & FVM_F_EDGE_EL) != 0)
+#define FVM_EDGE_MASKED ((FVM_FLAGS & FVM_F_EDGE_MASK) != 0)
+#define FVM_STAGE_X ((FVM_FLAGS & FVM_F_X) != 0)
+#define FVM_STAGE_U ((FVM_FLAGS & FVM_F_U) != 0)
+#define FVM_STAGE_CV ((FVM_FLAGS & FVM_F_CV) != 0)
+#define FVM_VERT_MASKED ((FVM_FLAGS & FVM_F_VMASK) != 0)
+#define FVM_HAS_DIRICHLET ((FVM_FLAGS & FVM_F_DIR) != 0)
+
+#define FVM_NCT (32 * FVM_CONSUMER_WARPS)  // consumer threads
+#define FVM_THREADS (FVM_NCT + 32)         // + one producer warp
+
+static_assert(!(FVM_EDGE_USES_X || FVM_VERT_USES_X) || FVM_STAGE_X, "FVM_F_X missing");
+static_assert(!(FVM_EDGE_USES_U || FVM_VERT_USES_U) || FVM_STAGE_U, "FVM_F_U missing");
+static_assert(!(FVM_EDGE_FACTORED && (FVM_EDGE_USES_EL || FVM_EDGE_MASKED)),
+              "ce factoring needs a slot-invariant functor");
 
 __device__ __forceinline__ unsigned fvm_smem_u32(const void* p) {
   return (unsigned)__cvta_generic_to_shared(p);
@@ -41,13 +60,16 @@ __device__ __forceinline__ unsigned fvm_smem_u32(const void* p) {
 
 __device__ __forceinline__ void fvm_mbar_init(void* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fvm_smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
 __device__ __forceinline__ void fvm_mbar_expect_tx(void* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fvm_smem_u32(bar)),
                "r"(bytes)
                : "memory");
+}
+
+__device__ __forceinline__ void fvm_mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fvm_smem_u32(bar)) : "memory");
 }
 
 // TMA 1-D bulk copy global -> shared (SASS: UBLKCP); 16B-aligned, size % 16 == 0
@@ -74,192 +96,348 @@ __device__ __forceinline__ void fvm_mbar_wait(void* bar, unsigned parity) {
       : "memory");
 }
 
-extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const FvmTileArgs a) {
-  extern __shared__ __align__(16) unsigned char fvm_smem[];
-  const int t = blockIdx.x;
-  const int r0 = a.tile_row[t];
-  const int r1 = a.tile_row[t + 1];
-  if (r0 >= r1) return;  // empty tile (a row heavier than the tile quantum precedes it)
-  const long long h0 = a.heptr[r0];
-  const long long h1 = a.heptr[r1];
-  const int s0 = a.indptr[r0];
-  const int nsl = a.indptr[r1] - s0;
-  const int nhe = (int)(h1 - h0);
-  const int nr = r1 - r0;
+// barrier among the consumer warps only (the producer warp never joins)
+__device__ __forceinline__ void fvm_consumer_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(FVM_NCT) : "memory");
+}
 
-  const FvmSmemLayout L =
-      fvm_smem_layout(a.max_he, a.max_slots, a.max_rows, FVM_EDGE_USES_EL, FVM_EDGE_MASKED);
-  void* bar = fvm_smem + L.bar;
-  const double* sm_ce = (const double*)(fvm_smem + L.ce);
-  const double* sm_el = (const double*)(fvm_smem + L.el);
-  const unsigned char* sm_mask = fvm_smem + L.mask;
-  double* pd = (double*)(fvm_smem + L.pd);
-  double* pc = (double*)(fvm_smem + L.pc);
-  unsigned short* srow = (unsigned short*)(fvm_smem + L.srow);
-  unsigned short* dpos = (unsigned short*)(fvm_smem + L.dpos);
+// One staged stream: `nbytes` bytes at global address g (any alignment) land in
+// a 16B-aligned shared buffer at byte offset `shift`.
+struct FvmStage {
+  const unsigned char* src;  // 16B-aligned global start
+  unsigned shift;            // offset of the first element inside the buffer
+  unsigned bytes;            // copy size, multiple of 16
+};
 
-  // ---- 1. TMA bulk load of the tile's half-edge streams -------------------
-  const long long ha = h0 & ~1LL;  // 16B-aligned start of the fp64 streams
-  const int sh = (int)(h0 - ha);   // 0 or 1: shift of half-edge 0 inside smem
-#if FVM_EDGE_MASKED
-  const long long hb = h0 & ~15LL;
-  const int shm = (int)(h0 - hb);
-#endif
-  if (threadIdx.x == 0) fvm_mbar_init(bar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0 && nhe > 0) {
-    const unsigned bytes = fvm_round16((unsigned)(h1 - ha) * 8u);
-    unsigned total = bytes;
+__device__ __forceinline__ FvmStage fvm_stage(const void* g, unsigned nbytes) {
+  FvmStage s;
+  const unsigned long long a = (unsigned long long)g;
+  s.shift = (unsigned)(a & 15ull);
+  s.src = (const unsigned char*)(a - s.shift);
+  s.bytes = nbytes ? fvm_round16(s.shift + nbytes) : 0u;
+  return s;
+}
+
+__device__ __forceinline__ unsigned fvm_shift(const void* g) {
+  return (unsigned)((unsigned long long)g & 15ull);
+}
+
+__device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemLayout& L,
+                                            unsigned char* stage, void* full,
+                                            const FvmTileDesc& d) {
+  const int v0 = a.row_base + d.r0;
+  *(FvmTileDesc*)(stage + L.desc) = d;
+  unsigned total = 0;
+  const FvmStage g_ce = fvm_stage(a.he_ce + d.h0, (unsigned)d.nhe * 8u);
+  const FvmStage g_col = fvm_stage(a.colidx + d.s0, (unsigned)d.nsl * 4u);
+  const FvmStage g_off = fvm_stage(a.slot_off + d.s0, (unsigned)d.nsl * 2u);
+  const FvmStage g_rp = fvm_stage(a.indptr + d.r0, (unsigned)(d.nr + 1) * 4u);
+  total += g_ce.bytes + g_col.bytes + g_off.bytes + g_rp.bytes;
 #if FVM_EDGE_USES_EL
-    total += bytes;
+  const FvmStage g_el = fvm_stage(a.he_el + d.h0, (unsigned)d.nhe * 8u);
+  total += g_el.bytes;
 #endif
 #if FVM_EDGE_MASKED
-    const unsigned mbytes = fvm_round16((unsigned)(h1 - hb));
-    total += mbytes;
+  const FvmStage g_mask = fvm_stage(a.he_mask + d.h0, (unsigned)d.nhe);
+  total += g_mask.bytes;
 #endif
-    fvm_mbar_expect_tx(bar, total);
-    fvm_bulk_g2s((void*)sm_ce, a.he_ce + ha, bytes, bar);
-#if FVM_EDGE_USES_EL
-    fvm_bulk_g2s((void*)sm_el, a.he_el + ha, bytes, bar);
+#if FVM_STAGE_CV
+  const FvmStage g_cv = fvm_stage(a.cv + v0, (unsigned)d.nr * 8u);
+  total += g_cv.bytes;
 #endif
-#if FVM_EDGE_MASKED
-    fvm_bulk_g2s((void*)sm_mask, a.he_mask + hb, mbytes, bar);
+#if FVM_STAGE_X
+  const FvmStage g_xy = fvm_stage(a.coords + (size_t)v0 * FVM_DIM, (unsigned)d.nr * 8u * FVM_DIM);
+  total += g_xy.bytes;
 #endif
-  }
-
-  // ---- 2. paint slot -> row while the copy is in flight -------------------
-  for (int r = threadIdx.x; r < nr; r += FVM_THREADS) {
-    const int b = a.indptr[r0 + r] - s0;
-    const int e = a.indptr[r0 + r + 1] - s0;
-    for (int s = b; s < e; ++s) srow[s] = (unsigned short)r;
-  }
-  __syncthreads();
-  if (nhe > 0) fvm_mbar_wait(bar, 0);
-
-  // ---- 3. slot-parallel fold ----------------------------------------------
-  for (int s = threadIdx.x; s < nsl; s += FVM_THREADS) {
-    const int lo = a.slot_off[s0 + s];
-    const int hi = (s + 1 < nsl) ? (int)a.slot_off[s0 + s + 1] : nhe;
-    const int r = srow[s];
-    if (lo == hi) {  // the diagonal slot owns no half-edge of its own
-      dpos[r] = (unsigned short)s;
-      pd[s] = 0.0;
-      pc[s] = 0.0;
-      continue;
-    }
-    const int row = a.row_base + r0 + r;
-    const int col = a.colidx[s0 + s];
-    double x00 = 0.0, x01 = 0.0, x02 = 0.0, x10 = 0.0, x11 = 0.0, x12 = 0.0;
-    double u0 = 0.0, u1 = 0.0;
-#if FVM_EDGE_USES_X
-    {
-      const double* p0 = a.coords + (size_t)row * FVM_DIM;
-      const double* p1 = a.coords + (size_t)col * FVM_DIM;
-      x00 = __ldg(p0);
-      x01 = __ldg(p0 + 1);
-      x10 = __ldg(p1);
-      x11 = __ldg(p1 + 1);
-#if FVM_DIM == 3
-      x02 = __ldg(p0 + 2);
-      x12 = __ldg(p1 + 2);
+#if FVM_STAGE_U
+  const FvmStage g_u = fvm_stage(a.u + v0, (unsigned)d.nr * 8u);
+  total += g_u.bytes;
 #endif
-    }
-#endif
-#if FVM_EDGE_USES_U
-    u0 = __ldg(a.u + row);
-    u1 = __ldg(a.u + col);
-#endif
-    double aD = 0.0, aO = 0.0, aC = 0.0;
-    for (int k = lo; k < hi; ++k) {
-      const double ce = sm_ce[sh + k];
-      double el = 0.0;
-      unsigned m = 0xffu;
-#if FVM_EDGE_USES_EL
-      el = sm_el[sh + k];
-#endif
-#if FVM_EDGE_MASKED
-      m = sm_mask[shm + k];
-#endif
-      double D = 0.0, O = 0.0, C = 0.0;
-      fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, el, m, D, O, C);
-      aD += D;
-      aO += O;
-      aC += C;
-    }
-    pd[s] = aD;
-    pc[s] = aC;
-#if FVM_MODE != FVM_MODE_RESIDUAL
-    {
 #if FVM_HAS_DIRICHLET
-      // Dirichlet rows keep their pattern but store explicit zeros off the diagonal
-      if (a.dir_id[row]) aO = 0.0;
+  const FvmStage g_dir = fvm_stage(a.dir_id + v0, (unsigned)d.nr);
+  total += g_dir.bytes;
 #endif
-      a.data[s0 + s] = aO;
-    }
-#endif
-  }
-  __syncthreads();
-
-  // ---- 4. row-parallel fold: diagonal slot, rhs / F, vertex term, Dirichlet
-  for (int r = threadIdx.x; r < nr; r += FVM_THREADS) {
-    const int b = a.indptr[r0 + r] - s0;
-    const int e = a.indptr[r0 + r + 1] - s0;
-    double sD = 0.0, sC = 0.0;
-    for (int s = b; s < e; ++s) {
-      sD += pd[s];
-      sC += pc[s];
-    }
-    const int row = a.row_base + r0 + r;
-    double x0 = 0.0, x1 = 0.0, x2 = 0.0, uu = 0.0, cvv = 0.0;
-#if FVM_VERT_USES_X
-    {
-      const double* p = a.coords + (size_t)row * FVM_DIM;
-      x0 = __ldg(p);
-      x1 = __ldg(p + 1);
-#if FVM_DIM == 3
-      x2 = __ldg(p + 2);
-#endif
-    }
-#endif
-#if FVM_VERT_USES_U
-    uu = __ldg(a.u + row);
-#endif
-#if FVM_VERT_USES_CV
-    cvv = __ldg(a.cv + row);
-#endif
-#if FVM_HAS_VERTEX
-    {
-      unsigned vm = 0xffu;
 #if FVM_VERT_MASKED
-      vm = a.vmask[row];
+  const FvmStage g_vm = fvm_stage(a.vmask + v0, (unsigned)d.nr);
+  total += g_vm.bytes;
 #endif
-      double VL = 0.0, VC = 0.0;
-      fvm_vertex(uu, cvv, x0, x1, x2, vm, VL, VC);
-      sD += VL;
-      sC += VC;
-    }
+  fvm_mbar_expect_tx(full, total);  // release: the descriptor store above is visible
+  if (g_ce.bytes) fvm_bulk_g2s(stage + L.ce, g_ce.src, g_ce.bytes, full);
+  if (g_col.bytes) fvm_bulk_g2s(stage + L.col, g_col.src, g_col.bytes, full);
+  if (g_off.bytes) fvm_bulk_g2s(stage + L.off, g_off.src, g_off.bytes, full);
+  fvm_bulk_g2s(stage + L.rowptr, g_rp.src, g_rp.bytes, full);
+#if FVM_EDGE_USES_EL
+  if (g_el.bytes) fvm_bulk_g2s(stage + L.el, g_el.src, g_el.bytes, full);
 #endif
-#if FVM_MODE == FVM_MODE_LINEAR
-    double out_vec = -sC;  // rhs = -(sum of affine parts)
-#else
-    double out_vec = sC;
+#if FVM_EDGE_MASKED
+  if (g_mask.bytes) fvm_bulk_g2s(stage + L.mask, g_mask.src, g_mask.bytes, full);
+#endif
+#if FVM_STAGE_CV
+  if (g_cv.bytes) fvm_bulk_g2s(stage + L.cv, g_cv.src, g_cv.bytes, full);
+#endif
+#if FVM_STAGE_X
+  if (g_xy.bytes) fvm_bulk_g2s(stage + L.xy, g_xy.src, g_xy.bytes, full);
+#endif
+#if FVM_STAGE_U
+  if (g_u.bytes) fvm_bulk_g2s(stage + L.u, g_u.src, g_u.bytes, full);
 #endif
 #if FVM_HAS_DIRICHLET
-    {
-      const int id = a.dir_id[row];
-      if (id) {
-        double dc = 0.0, dv = 0.0;
-        fvm_dirichlet(id, uu, x0, x1, x2, dc, dv);
-        sD = dc;       // row := coeff * e_row
-        out_vec = dv;  // rhs := -affine (linear) / F := condition(u) (residual)
+  if (g_dir.bytes) fvm_bulk_g2s(stage + L.dir, g_dir.src, g_dir.bytes, full);
+#endif
+#if FVM_VERT_MASKED
+  if (g_vm.bytes) fvm_bulk_g2s(stage + L.vmask, g_vm.src, g_vm.bytes, full);
+#endif
+}
+
+__device__ __forceinline__ FvmTileDesc fvm_load_desc(const FvmTileDesc* g) {
+  FvmTileDesc d;
+  const int4 d0 = __ldg((const int4*)g), d1 = __ldg((const int4*)g + 1);
+  ((int4*)&d)[0] = d0;
+  ((int4*)&d)[1] = d1;
+  return d;
+}
+
+extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const FvmTileArgs a) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const FvmSmemLayout L =
+      fvm_smem_layout(a.max_he, a.max_slots, a.max_rows, FVM_DIM, FVM_FLAGS, FVM_MODE, FVM_STAGES);
+  unsigned long long* full = (unsigned long long*)(sm + L.bar);
+  unsigned long long* empty = full + FVM_STAGES;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FVM_STAGES; ++i) {
+      fvm_mbar_init(full + i, 1);                    // the producer's expect_tx arrival
+      fvm_mbar_init(empty + i, FVM_CONSUMER_WARPS);  // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (threadIdx.x < 32) {
+    // ===================== producer warp (one elected lane) ===================
+    if (threadIdx.x == 0) {
+      int t = blockIdx.x;
+      if (t < a.ntiles) {
+        FvmTileDesc d = fvm_load_desc(a.tiles + t);
+        for (int it = 0; t < a.ntiles; ++it) {
+          const int st = it % FVM_STAGES;
+          const int tn = t + gridDim.x;
+          FvmTileDesc dn = d;
+          if (tn < a.ntiles) dn = fvm_load_desc(a.tiles + tn);  // next descriptor in flight
+          if (it >= FVM_STAGES) fvm_mbar_wait(empty + st, ((it / FVM_STAGES) - 1) & 1);
+          fvm_produce(a, L, sm + L.stage0 + st * L.stage_bytes, full + st, d);
+          d = dn;
+          t = tn;
+        }
       }
     }
-#endif
+    return;
+  }
+
+  // ========================= consumer warps ==================================
+  const int ct = threadIdx.x - 32;  // consumer thread id
 #if FVM_MODE != FVM_MODE_RESIDUAL
-    a.data[s0 + dpos[r]] = sD;
+  double* pd = (double*)(sm + L.pd);
 #endif
 #if FVM_MODE != FVM_MODE_JACOBIAN
-    a.vec[r0 + r] = out_vec;
+  double* pc = (double*)(sm + L.pc);
 #endif
+  unsigned short* srow = (unsigned short*)(sm + L.srow);
+  unsigned short* dpos = (unsigned short*)(sm + L.dpos);
+
+  int it = 0;
+  for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+    const int st = it % FVM_STAGES;
+    unsigned char* stage = sm + L.stage0 + st * L.stage_bytes;
+    fvm_mbar_wait(full + st, (it / FVM_STAGES) & 1);
+    const FvmTileDesc d = *(const FvmTileDesc*)(stage + L.desc);
+    const int v0 = a.row_base + d.r0;  // first vertex of the tile
+
+    const double* s_ce = (const double*)(stage + L.ce + fvm_shift(a.he_ce + d.h0));
+    const int* s_col = (const int*)(stage + L.col + fvm_shift(a.colidx + d.s0));
+    const unsigned short* s_off =
+        (const unsigned short*)(stage + L.off + fvm_shift(a.slot_off + d.s0));
+    const int* s_rp = (const int*)(stage + L.rowptr + fvm_shift(a.indptr + d.r0));
+#if FVM_EDGE_USES_EL
+    const double* s_el = (const double*)(stage + L.el + fvm_shift(a.he_el + d.h0));
+#endif
+#if FVM_EDGE_MASKED
+    const unsigned char* s_mask = stage + L.mask + fvm_shift(a.he_mask + d.h0);
+#endif
+#if FVM_STAGE_CV
+    const double* s_cv = (const double*)(stage + L.cv + fvm_shift(a.cv + v0));
+#endif
+#if FVM_STAGE_X
+    const double* s_xy = (const double*)(stage + L.xy + fvm_shift(a.coords + (size_t)v0 * FVM_DIM));
+#endif
+#if FVM_STAGE_U
+    const double* s_u = (const double*)(stage + L.u + fvm_shift(a.u + v0));
+#endif
+#if FVM_HAS_DIRICHLET
+    const unsigned char* s_dir = stage + L.dir + fvm_shift(a.dir_id + v0);
+#endif
+#if FVM_VERT_MASKED
+    const unsigned char* s_vm = stage + L.vmask + fvm_shift(a.vmask + v0);
+#endif
+
+    // ---- 2. paint slot -> row ------------------------------------------------
+    for (int r = ct; r < d.nr; r += FVM_NCT) {
+      const int b = s_rp[r] - d.s0;
+      const int e = s_rp[r + 1] - d.s0;
+      for (int s = b; s < e; ++s) srow[s] = (unsigned short)r;
+    }
+    fvm_consumer_sync();  // also: every consumer has left phase 4 of the previous tile
+
+    // ---- 3. slot-parallel fold --------------------------------------------
+    for (int s = ct; s < d.nsl; s += FVM_NCT) {
+      const int lo = s_off[s];
+      const int hi = (s + 1 < d.nsl) ? (int)s_off[s + 1] : d.nhe;
+      const int r = srow[s];
+      if (lo == hi) {  // the diagonal slot owns no half-edge of its own
+        dpos[r] = (unsigned short)s;
+#if FVM_MODE != FVM_MODE_RESIDUAL
+        pd[s] = 0.0;
+#endif
+#if FVM_MODE != FVM_MODE_JACOBIAN
+        pc[s] = 0.0;
+#endif
+        continue;
+      }
+      const int col = s_col[s];
+      const unsigned cl = (unsigned)(col - v0);  // tile-local column, if inside
+      double x00 = 0.0, x01 = 0.0, x02 = 0.0, x10 = 0.0, x11 = 0.0, x12 = 0.0;
+      double u0 = 0.0, u1 = 0.0;
+#if FVM_EDGE_USES_X
+      if (cl < (unsigned)d.nr) {
+        x10 = s_xy[cl * FVM_DIM];
+        x11 = s_xy[cl * FVM_DIM + 1];
+#if FVM_DIM == 3
+        x12 = s_xy[cl * FVM_DIM + 2];
+#endif
+      } else {
+        const double* p1 = a.coords + (size_t)col * FVM_DIM;
+#if FVM_DIM == 2
+        const double2 q = __ldg((const double2*)p1);
+        x10 = q.x;
+        x11 = q.y;
+#else
+        x10 = __ldg(p1);
+        x11 = __ldg(p1 + 1);
+        x12 = __ldg(p1 + 2);
+#endif
+      }
+      x00 = s_xy[r * FVM_DIM];
+      x01 = s_xy[r * FVM_DIM + 1];
+#if FVM_DIM == 3
+      x02 = s_xy[r * FVM_DIM + 2];
+#endif
+#endif
+#if FVM_EDGE_USES_U
+      u1 = (cl < (unsigned)d.nr) ? s_u[cl] : __ldg(a.u + col);
+      u0 = s_u[r];
+#endif
+      double aD = 0.0, aO = 0.0, aC = 0.0;
+#if FVM_EDGE_FACTORED
+      // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
+      double ce = 0.0;
+      for (int k = lo; k < hi; ++k) ce += s_ce[k];
+      fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, 0.0, 0xffu, aD, aO, aC);
+#else
+      for (int k = lo; k < hi; ++k) {
+        const double ce = s_ce[k];
+        double el = 0.0;
+        unsigned m = 0xffu;
+#if FVM_EDGE_USES_EL
+        el = s_el[k];
+#endif
+#if FVM_EDGE_MASKED
+        m = s_mask[k];
+#endif
+        double D = 0.0, O = 0.0, C = 0.0;
+        fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, el, m, D, O, C);
+        aD += D;
+        aO += O;
+        aC += C;
+      }
+#endif
+#if FVM_MODE != FVM_MODE_JACOBIAN
+      pc[s] = aC;
+#endif
+#if FVM_MODE != FVM_MODE_RESIDUAL
+      pd[s] = aD;
+#if FVM_HAS_DIRICHLET
+      // Dirichlet rows keep their pattern but store explicit zeros off the diagonal
+      if (s_dir[r]) aO = 0.0;
+#endif
+      a.data[d.s0 + s] = aO;
+#endif
+    }
+    fvm_consumer_sync();
+
+    // ---- 4. row-parallel fold: diagonal slot, rhs / F, vertex term, Dirichlet
+    for (int r = ct; r < d.nr; r += FVM_NCT) {
+      const int b = s_rp[r] - d.s0;
+      const int e = s_rp[r + 1] - d.s0;
+      double sD = 0.0, sC = 0.0;
+      for (int s = b; s < e; ++s) {
+#if FVM_MODE != FVM_MODE_RESIDUAL
+        sD += pd[s];
+#endif
+#if FVM_MODE != FVM_MODE_JACOBIAN
+        sC += pc[s];
+#endif
+      }
+      double x0 = 0.0, x1 = 0.0, x2 = 0.0, uu = 0.0, cvv = 0.0;
+#if FVM_VERT_USES_X
+      x0 = s_xy[r * FVM_DIM];
+      x1 = s_xy[r * FVM_DIM + 1];
+#if FVM_DIM == 3
+      x2 = s_xy[r * FVM_DIM + 2];
+#endif
+#endif
+#if FVM_VERT_USES_U
+      uu = s_u[r];
+#endif
+#if FVM_STAGE_CV
+      cvv = s_cv[r];
+#endif
+#if FVM_HAS_VERTEX
+      {
+        unsigned vm = 0xffu;
+#if FVM_VERT_MASKED
+        vm = s_vm[r];
+#endif
+        double VL = 0.0, VC = 0.0;
+        fvm_vertex(uu, cvv, x0, x1, x2, vm, VL, VC);
+        sD += VL;
+        sC += VC;
+      }
+#endif
+#if FVM_MODE == FVM_MODE_LINEAR
+      double out_vec = -sC;  // rhs = -(sum of affine parts)
+#else
+      double out_vec = sC;
+#endif
+#if FVM_HAS_DIRICHLET
+      {
+        const int id = s_dir[r];
+        if (id) {
+          double dc = 0.0, dv = 0.0;
+          fvm_dirichlet(id, uu, x0, x1, x2, dc, dv);
+          sD = dc;       // row := coeff * e_row
+          out_vec = dv;  // rhs := -affine (linear) / F := condition(u) (residual)
+        }
+      }
+#endif
+#if FVM_MODE != FVM_MODE_RESIDUAL
+      a.data[d.s0 + dpos[r]] = sD;
+#endif
+#if FVM_MODE != FVM_MODE_JACOBIAN
+      a.vec[d.r0 + r] = out_vec;
+#endif
+    }
+    // ---- release the stage to the producer (all lanes of this warp are done)
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) fvm_mbar_arrive(empty + st);
   }
 }

@@ -16,8 +16,6 @@ import numpy
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfvm_b200.so")
 
-KF_USES_EL = 1
-KF_EDGE_MASKED = 2
 
 
 class FvmError(RuntimeError):
@@ -42,6 +40,18 @@ class MeshDesc(ctypes.Structure):
         ("coords", c_void_p),
         ("control_volumes", c_void_p),
         ("tile_quantum", c_int32),
+    ]
+
+
+class KernelOpts(ctypes.Structure):
+    # mirrors fvm_kernel_opts in include/fvm_b200.h
+    _fields_ = [
+        ("mode", c_int32),
+        ("flags", c_uint),
+        ("fmad", c_int32),
+        ("consumer_warps", c_int32),
+        ("stages", c_int32),
+        ("ctas_per_sm", c_int32),
     ]
 
 
@@ -71,7 +81,11 @@ SYMBOLS = {
     "fvm_mesh_get_pattern": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fvm_mesh_pattern_dev": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
     "fvm_mesh_update_geometry": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
-    "fvm_kernel_create": (c_int, [c_void_p, c_char_p, c_int, c_uint, c_int, POINTER(c_void_p)]),
+    "fvm_kernel_create": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_void_p)]),
+    "fvm_kernel_launch_shape": (
+        c_int,
+        [c_void_p, c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)],
+    ),
     "fvm_kernel_destroy": (c_int, [c_void_p]),
     "fvm_kernel_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "fvm_kernel_source": (c_int, [c_char_p, c_char_p, c_size_t, POINTER(c_size_t)]),
@@ -212,13 +226,18 @@ class Engine:
         key = (hashlib.sha256(functors.source.encode()).hexdigest(), functors.mode, bool(fmad))
         k = self._kernels.get(key)
         if k is None:
-            flags = (KF_USES_EL if functors.uses_el else 0) | (
-                KF_EDGE_MASKED if functors.edge_masked else 0
-            )
             h = c_void_p()
+            opts = KernelOpts(
+                mode=functors.mode,
+                flags=functors.flags,
+                fmad=int(fmad),
+                consumer_warps=functors.consumer_warps,
+                stages=functors.stages,
+                ctas_per_sm=functors.ctas_per_sm,
+            )
             self._ck(
                 self.lib.fvm_kernel_create(
-                    self.ctx, functors.source.encode(), functors.mode, flags, int(fmad), byref(h)
+                    self.ctx, functors.source.encode(), ctypes.cast(ctypes.pointer(opts), c_void_p), byref(h)
                 )
             )
             k = Kernel(self, h, functors)
@@ -242,10 +261,19 @@ class Kernel:
     def __init__(self, eng, handle, functors):
         self.eng, self.handle, self.functors = eng, handle, functors
 
-    def info(self):
+    def info(self, dmesh=None):
         r, s, t = c_int(), c_int(), c_int()
         self.eng._ck(self.eng.lib.fvm_kernel_info(self.handle, byref(r), byref(s), byref(t)))
-        return {"regs": r.value, "static_smem": s.value, "max_threads": t.value}
+        out = {"regs": r.value, "static_smem": s.value, "max_threads": t.value}
+        if dmesh is not None:
+            g, b, m = c_int(), c_int(), c_int()
+            self.eng._ck(
+                self.eng.lib.fvm_kernel_launch_shape(
+                    self.handle, dmesh.handle, byref(g), byref(b), byref(m)
+                )
+            )
+            out.update(grid=g.value, block=b.value, smem=m.value)
+        return out
 
 
 def _mesh_arrays(mesh):
@@ -266,6 +294,7 @@ class DeviceMesh:
     cached per mesh object, like meshplex caches its own derived arrays."""
 
     def __init__(self, eng, mesh, rec_mask=None, need_el=True, row_range=None, tile_quantum=0):
+        tile_quantum = tile_quantum or int(os.environ.get("FVM_TILE_QUANTUM", "0"))
         self.eng = eng
         idx, coords, dim = _mesh_arrays(mesh)
         self.dim = dim
