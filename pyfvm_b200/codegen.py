@@ -19,9 +19,14 @@ MODE_LINEAR, MODE_RESIDUAL, MODE_JACOBIAN = 0, 1, 2
 F_EDGE_EL, F_EDGE_MASK, F_X, F_U, F_CV, F_VMASK, F_DIR = 1, 2, 4, 8, 16, 32, 64
 
 
-def tuning():
-    """Launch-shape knobs of the tile kernel (env overrides are for experiments)."""
+def tuning(cell_dim=2):
+    """Launch-shape knobs of the tile kernel (env overrides are for experiments).
+
+    ``group`` = lanes that share one matrix row.  It is fixed per cell type
+    (triangles: 1, tetrahedra: 8) because it shapes the floating-point fold of a
+    row: the same mesh must fold the same way on one GPU and on many."""
     return {
+        "group": int(os.environ.get("FVM_GROUP", "1" if cell_dim == 2 else "8")),
         "consumer_warps": int(os.environ.get("FVM_CONSUMER_WARPS", "8")),
         "stages": int(os.environ.get("FVM_STAGES", "2")),
         "ctas_per_sm": int(os.environ.get("FVM_CTAS_PER_SM", "0")),
@@ -121,6 +126,7 @@ class Functors:
     consumer_warps: int
     stages: int
     ctas_per_sm: int
+    group: int
     factored: bool
     uses_el: bool
     uses_x: bool
@@ -143,7 +149,7 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
     flat_e = [e for ex in edge_exprs for e in ex]
     flat_v = [e for ex in vert_exprs + dir_exprs for e in ex]
     xv = lo.X0 + lo.X1
-    tune = tune or tuning()
+    tune = {**tuning(), **(tune or {})}
     edge_x, vert_x = _uses(flat_e, xv), _uses(flat_v, lo.XV)
     edge_u, vert_u = _uses(flat_e, [lo.UK0, lo.UK1]), _uses(flat_v, [lo.UK0])
     flags = 0
@@ -170,6 +176,7 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         "FVM_FLAGS": f"{flags}u",
         "FVM_CONSUMER_WARPS": tune["consumer_warps"],
         "FVM_STAGES": tune["stages"],
+        "FVM_GROUP": tune["group"],
         "FVM_EDGE_FACTORED": int(factored),
         "FVM_EDGE_USES_X": int(edge_x),
         "FVM_EDGE_USES_U": int(edge_u),
@@ -184,6 +191,8 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         raise ValueError(f"undefined functions cannot be lowered to device code: {sorted(bad)}")
 
     L = [f"// generated by pyfvm_b200.codegen (mode {mode}); do not edit"]
+    if os.environ.get("FVM_DEBUG_SKIP_COMPUTE"):
+        L.append("#define FVM_DEBUG_SKIP_COMPUTE 1")
     L += [f"#define {k} {v}" for k, v in defs.items()]
     L.append("")
     L.append(
@@ -228,6 +237,7 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         consumer_warps=tune["consumer_warps"],
         stages=tune["stages"],
         ctas_per_sm=tune["ctas_per_sm"],
+        group=tune["group"],
         factored=factored,
         uses_el=bool(flags & F_EDGE_EL),
         uses_x=bool(flags & F_X),

@@ -15,6 +15,17 @@ struct FvmTileDesc {  // 32 bytes, one per tile
   int nhe, pad;
 };
 
+// Dynamic shared-memory carve-up of one CTA, identical on host and device:
+//   [full/empty mbarriers][stage 0][stage 1]...[out 0][out 1]
+// The stream offsets (desc .. vmask) are relative to the start of a stage.
+// Every staged stream gets 16 spare bytes: its bulk copy starts at the 16B
+// boundary below the first element and is rounded up to 16B.
+struct FvmSmemLayout {
+  unsigned bar, stage0, stage_bytes;
+  unsigned desc, ce, el, mask, col, off, rowptr, cv, xy, u, dir, vmask;  // within a stage
+  unsigned out, out_bytes, total;  // double-buffered CSR-value staging (row group < 4)
+};
+
 struct FvmTileArgs {
   const FvmTileDesc* tiles;        // [ntiles]
   const int* indptr;               // [nrows+1] CSR row pointer
@@ -35,6 +46,7 @@ struct FvmTileArgs {
   int max_he;                      // largest tile: half-edges
   int max_slots;                   //               slots
   int max_rows;                    //               rows
+  struct FvmSmemLayout L;          // shared-memory carve-up (host: fvm_smem_layout)
 };
 
 #define FVM_MODE_LINEAR 0    // matrix values + rhs (discretize_linear)
@@ -50,17 +62,6 @@ struct FvmTileArgs {
 #define FVM_F_VMASK 32u     // vertex terms carry vertex-subdomain bits
 #define FVM_F_DIR 64u       // Dirichlet conditions present
 
-// Dynamic shared-memory carve-up of one CTA, identical on host and device:
-//   [full/empty mbarriers][stage 0][stage 1]...[scratch: pd pc srow dpos]
-// The stream offsets (desc .. vmask) are relative to the start of a stage.
-// Every staged stream gets 16 spare bytes: its bulk copy starts at the 16B
-// boundary below the first element and is rounded up to 16B.
-struct FvmSmemLayout {
-  unsigned bar, stage0, stage_bytes;
-  unsigned desc, ce, el, mask, col, off, rowptr, cv, xy, u, dir, vmask;  // within a stage
-  unsigned pd, pc, srow, dpos, total;
-};
-
 #ifdef __CUDACC__
 #define FVM_HD __host__ __device__
 #else
@@ -70,7 +71,7 @@ struct FvmSmemLayout {
 FVM_HD inline unsigned fvm_round16(unsigned x) { return (x + 15u) & ~15u; }
 
 FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_rows, int dim,
-                                            unsigned flags, int mode, int stages) {
+                                            unsigned flags, int mode, int stages, int group) {
   FvmSmemLayout L;
   const unsigned he = (unsigned)max_he, sl = (unsigned)max_slots, nr = (unsigned)max_rows;
   unsigned o = 0;  // within a stage
@@ -90,10 +91,9 @@ FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_r
   L.bar = 0;
   L.stage0 = fvm_round16(16u * (unsigned)stages);  // 2 x 8B mbarriers per stage
   o = L.stage0 + L.stage_bytes * (unsigned)stages;
-  L.pd = o;     o += (mode != FVM_MODE_RESIDUAL) ? fvm_round16(sl * 8u) : 0u;
-  L.pc = o;     o += (mode != FVM_MODE_JACOBIAN) ? fvm_round16(sl * 8u) : 0u;
-  L.srow = o;   o += fvm_round16(sl * 2u);
-  L.dpos = o;   o += fvm_round16(nr * 2u);
+  L.out = o;
+  L.out_bytes = (group < 4 && mode != FVM_MODE_RESIDUAL) ? fvm_round16(sl * 8u) : 0u;
+  o += 2u * L.out_bytes;
   L.total = o;
   return L;
 }

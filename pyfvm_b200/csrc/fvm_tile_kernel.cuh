@@ -6,7 +6,7 @@
 //   FVM_MODE_JACOBIAN : jacobian.get_linear_operator(u0) values         [README:116]
 //
 // It is compiled at run time by NVRTC after a generated prelude that defines
-//   FVM_MODE, FVM_DIM, FVM_FLAGS (FVM_F_* bits), FVM_CONSUMER_WARPS, FVM_STAGES,
+//   FVM_MODE, FVM_DIM, FVM_FLAGS (FVM_F_* bits), FVM_CONSUMER_WARPS, FVM_STAGES, FVM_GROUP,
 //   FVM_EDGE_USES_X / _U, FVM_VERT_USES_X / _U, FVM_HAS_VERTEX, FVM_EDGE_FACTORED
 // and the three sympy-printed device functors
 //   fvm_edge(uk0, uk1, x0_0..2, x1_0..2, edge_ce_ratio, edge_length, mask, &D, &O, &C)
@@ -23,16 +23,19 @@
 //                    tile needs -- ce_ratio / edge_length / mask per half-edge,
 //                    column + offset per slot, row pointer / coords / cv / u /
 //                    Dirichlet id per row -- one or more tiles ahead of the math;
-//   consumer warps : (2) paint slot -> row, (3) slot-parallel: thread s folds the
-//                    contributions of CSR slot s from shared memory in half-edge
-//                    order (deterministic, atomic-free), gathering x/u only for
-//                    columns outside the tile, and stores data[s] coalesced,
-//                    (4) row-parallel: thread r folds the per-slot partials of its
-//                    row into the diagonal slot and rhs/F, adds the vertex term
-//                    and applies the Dirichlet row replacement in the same pass.
-// The fold order of a slot/row depends only on the row's own half-edge order,
-// never on tile boundaries or the grid size, so a row-partitioned multi-GPU run
-// is bit-identical to the single-GPU run.
+//   consumer warps : a group of FVM_GROUP lanes owns one matrix row: lane j folds
+//                    the row's CSR slots j, j+G, ... -- each slot's contributions in
+//                    half-edge order out of shared memory (deterministic,
+//                    atomic-free), gathering x/u only for columns outside the
+//                    tile -- and keeps the row's diagonal / rhs sums in registers;
+//                    a fixed xor-shuffle tree joins the lanes; lane 0 adds the
+//                    vertex term and applies the Dirichlet row replacement in the
+//                    same pass.  CSR values leave through a double-buffered
+//                    shared staging array (FVM_GROUP < 4) so that the global
+//                    stores are coalesced, or directly (FVM_GROUP >= 4).
+// The fold order of a slot/row depends only on the row's own half-edge order and
+// FVM_GROUP (fixed per cell type), never on tile boundaries or the grid size, so
+// a row-partitioned multi-GPU run is bit-identical to the single-GPU run.
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -47,10 +50,13 @@
 #define FVM_HAS_DIRICHLET ((FVM_FLAGS & FVM_F_DIR) != 0)
 
 #define FVM_NCT (32 * FVM_CONSUMER_WARPS)  // consumer threads
+#define FVM_STAGE_OUT (FVM_GROUP < 4 && FVM_MODE != FVM_MODE_RESIDUAL)
 #define FVM_THREADS (FVM_NCT + 32)         // + one producer warp
 
 static_assert(!(FVM_EDGE_USES_X || FVM_VERT_USES_X) || FVM_STAGE_X, "FVM_F_X missing");
 static_assert(!(FVM_EDGE_USES_U || FVM_VERT_USES_U) || FVM_STAGE_U, "FVM_F_U missing");
+static_assert(FVM_GROUP >= 1 && FVM_GROUP <= 32 && (FVM_GROUP & (FVM_GROUP - 1)) == 0,
+              "FVM_GROUP must be a power of two");
 static_assert(!(FVM_EDGE_FACTORED && (FVM_EDGE_USES_EL || FVM_EDGE_MASKED)),
               "ce factoring needs a slot-invariant functor");
 
@@ -94,6 +100,26 @@ __device__ __forceinline__ void fvm_mbar_wait(void* bar, unsigned parity) {
       "}\n" ::"r"(fvm_smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+
+// same, for the producer: back off between polls so the spin does not take
+// issue slots from the consumer warps of this SM sub-partition
+__device__ __forceinline__ void fvm_mbar_wait_backoff(void* bar, unsigned parity) {
+  const unsigned addr = fvm_smem_u32(bar);
+  for (;;) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(256);
+  }
 }
 
 // barrier among the consumer warps only (the producer warp never joins)
@@ -199,8 +225,7 @@ __device__ __forceinline__ FvmTileDesc fvm_load_desc(const FvmTileDesc* g) {
 
 extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const FvmTileArgs a) {
   extern __shared__ __align__(16) unsigned char sm[];
-  const FvmSmemLayout L =
-      fvm_smem_layout(a.max_he, a.max_slots, a.max_rows, FVM_DIM, FVM_FLAGS, FVM_MODE, FVM_STAGES);
+  const FvmSmemLayout L = a.L;  // computed by the host (fvm_smem_layout)
   unsigned long long* full = (unsigned long long*)(sm + L.bar);
   unsigned long long* empty = full + FVM_STAGES;
 
@@ -224,7 +249,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
           const int tn = t + gridDim.x;
           FvmTileDesc dn = d;
           if (tn < a.ntiles) dn = fvm_load_desc(a.tiles + tn);  // next descriptor in flight
-          if (it >= FVM_STAGES) fvm_mbar_wait(empty + st, ((it / FVM_STAGES) - 1) & 1);
+          if (it >= FVM_STAGES) fvm_mbar_wait_backoff(empty + st, ((it / FVM_STAGES) - 1) & 1);
           fvm_produce(a, L, sm + L.stage0 + st * L.stage_bytes, full + st, d);
           d = dn;
           t = tn;
@@ -235,15 +260,10 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
   }
 
   // ========================= consumer warps ==================================
-  const int ct = threadIdx.x - 32;  // consumer thread id
-#if FVM_MODE != FVM_MODE_RESIDUAL
-  double* pd = (double*)(sm + L.pd);
-#endif
-#if FVM_MODE != FVM_MODE_JACOBIAN
-  double* pc = (double*)(sm + L.pc);
-#endif
-  unsigned short* srow = (unsigned short*)(sm + L.srow);
-  unsigned short* dpos = (unsigned short*)(sm + L.dpos);
+  const int ct = threadIdx.x - 32;     // consumer thread id
+  const int gl = ct & (FVM_GROUP - 1);  // lane within the row group
+  const int gi = ct / FVM_GROUP;        // row group id
+  constexpr int NG = FVM_NCT / FVM_GROUP;
 
   int it = 0;
   for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
@@ -279,165 +299,180 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
 #if FVM_VERT_MASKED
     const unsigned char* s_vm = stage + L.vmask + fvm_shift(a.vmask + v0);
 #endif
-
-    // ---- 2. paint slot -> row ------------------------------------------------
-    for (int r = ct; r < d.nr; r += FVM_NCT) {
-      const int b = s_rp[r] - d.s0;
-      const int e = s_rp[r + 1] - d.s0;
-      for (int s = b; s < e; ++s) srow[s] = (unsigned short)r;
-    }
-    fvm_consumer_sync();  // also: every consumer has left phase 4 of the previous tile
-
-    // ---- 3. slot-parallel fold --------------------------------------------
-    for (int s = ct; s < d.nsl; s += FVM_NCT) {
-      const int lo = s_off[s];
-      const int hi = (s + 1 < d.nsl) ? (int)s_off[s + 1] : d.nhe;
-      const int r = srow[s];
-      if (lo == hi) {  // the diagonal slot owns no half-edge of its own
-        dpos[r] = (unsigned short)s;
-#if FVM_MODE != FVM_MODE_RESIDUAL
-        pd[s] = 0.0;
+#if FVM_STAGE_OUT
+    double* out = (double*)(sm + L.out + (unsigned)(it & 1) * L.out_bytes);
 #endif
-#if FVM_MODE != FVM_MODE_JACOBIAN
-        pc[s] = 0.0;
+
+#ifdef FVM_DEBUG_SKIP_COMPUTE  // experiment: stream the tiles, do no math (results are garbage)
+    if (false)
 #endif
-        continue;
+    for (int g0 = 0; g0 < d.nr; g0 += NG) {  // trip count uniform over the consumer warps
+      const int g = g0 + gi;                 // row of this lane group (tile-local)
+      const bool live = g < d.nr;
+      int b = 0, e = 0;
+      if (live) {
+        b = s_rp[g] - d.s0;
+        e = s_rp[g + 1] - d.s0;
       }
-      const int col = s_col[s];
-      const unsigned cl = (unsigned)(col - v0);  // tile-local column, if inside
-      double x00 = 0.0, x01 = 0.0, x02 = 0.0, x10 = 0.0, x11 = 0.0, x12 = 0.0;
-      double u0 = 0.0, u1 = 0.0;
-#if FVM_EDGE_USES_X
-      if (cl < (unsigned)d.nr) {
-        x10 = s_xy[cl * FVM_DIM];
-        x11 = s_xy[cl * FVM_DIM + 1];
-#if FVM_DIM == 3
-        x12 = s_xy[cl * FVM_DIM + 2];
-#endif
-      } else {
-        const double* p1 = a.coords + (size_t)col * FVM_DIM;
+      double x00 = 0.0, x01 = 0.0, x02 = 0.0, u0 = 0.0;
+      int dir = 0;
+      if (live) {
+#if FVM_STAGE_X
 #if FVM_DIM == 2
-        const double2 q = __ldg((const double2*)p1);
-        x10 = q.x;
-        x11 = q.y;
+        const double2 q0 = *(const double2*)(s_xy + 2 * g);
+        x00 = q0.x;
+        x01 = q0.y;
 #else
-        x10 = __ldg(p1);
-        x11 = __ldg(p1 + 1);
-        x12 = __ldg(p1 + 2);
+        x00 = s_xy[3 * g];
+        x01 = s_xy[3 * g + 1];
+        x02 = s_xy[3 * g + 2];
+#endif
+#endif
+#if FVM_STAGE_U
+        u0 = s_u[g];
+#endif
+#if FVM_HAS_DIRICHLET
+        dir = s_dir[g];
 #endif
       }
-      x00 = s_xy[r * FVM_DIM];
-      x01 = s_xy[r * FVM_DIM + 1];
-#if FVM_DIM == 3
-      x02 = s_xy[r * FVM_DIM + 2];
+      double sD = 0.0, sC = 0.0;  // this lane's share of the row's diagonal / rhs sums
+      int ds = -1;                // the row's diagonal slot, seen by exactly one lane
+      for (int s = b + gl; s < e; s += FVM_GROUP) {
+        const int lo = s_off[s];
+        const int hi = (s + 1 < d.nsl) ? (int)s_off[s + 1] : d.nhe;
+        if (lo == hi) {  // the diagonal slot owns no half-edge of its own
+          ds = s;
+          continue;
+        }
+        const int col = s_col[s];
+        const unsigned cl = (unsigned)(col - v0);  // tile-local column, if inside
+        double x10 = 0.0, x11 = 0.0, x12 = 0.0, u1 = 0.0;
+#if FVM_EDGE_USES_X
+        if (cl < (unsigned)d.nr) {
+#if FVM_DIM == 2
+          const double2 q = *(const double2*)(s_xy + 2 * cl);
+          x10 = q.x;
+          x11 = q.y;
+#else
+          x10 = s_xy[3 * cl];
+          x11 = s_xy[3 * cl + 1];
+          x12 = s_xy[3 * cl + 2];
 #endif
+        } else {
+          const double* p1 = a.coords + (size_t)col * FVM_DIM;
+#if FVM_DIM == 2
+          const double2 q = __ldg((const double2*)p1);
+          x10 = q.x;
+          x11 = q.y;
+#else
+          x10 = __ldg(p1);
+          x11 = __ldg(p1 + 1);
+          x12 = __ldg(p1 + 2);
+#endif
+        }
 #endif
 #if FVM_EDGE_USES_U
-      u1 = (cl < (unsigned)d.nr) ? s_u[cl] : __ldg(a.u + col);
-      u0 = s_u[r];
+        u1 = (cl < (unsigned)d.nr) ? s_u[cl] : __ldg(a.u + col);
 #endif
-      double aD = 0.0, aO = 0.0, aC = 0.0;
+        double aD = 0.0, aO = 0.0, aC = 0.0;
 #if FVM_EDGE_FACTORED
-      // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
-      double ce = 0.0;
-      for (int k = lo; k < hi; ++k) ce += s_ce[k];
-      fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, 0.0, 0xffu, aD, aO, aC);
+        // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
+        double ce = s_ce[lo];
+        if (hi - lo > 1) {
+          ce += s_ce[lo + 1];
+#pragma unroll 1
+          for (int k = lo + 2; k < hi; ++k) ce += s_ce[k];
+        }
+        fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, 0.0, 0xffu, aD, aO, aC);
 #else
-      for (int k = lo; k < hi; ++k) {
-        const double ce = s_ce[k];
-        double el = 0.0;
-        unsigned m = 0xffu;
+#pragma unroll 1
+        for (int k = lo; k < hi; ++k) {
+          const double ce = s_ce[k];
+          double el = 0.0;
+          unsigned m = 0xffu;
 #if FVM_EDGE_USES_EL
-        el = s_el[k];
+          el = s_el[k];
 #endif
 #if FVM_EDGE_MASKED
-        m = s_mask[k];
+          m = s_mask[k];
 #endif
-        double D = 0.0, O = 0.0, C = 0.0;
-        fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, el, m, D, O, C);
-        aD += D;
-        aO += O;
-        aC += C;
-      }
+          double D = 0.0, O = 0.0, C = 0.0;
+          fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, el, m, D, O, C);
+          aD += D;
+          aO += O;
+          aC += C;
+        }
 #endif
-#if FVM_MODE != FVM_MODE_JACOBIAN
-      pc[s] = aC;
-#endif
+        sD += aD;
+        sC += aC;
 #if FVM_MODE != FVM_MODE_RESIDUAL
-      pd[s] = aD;
-#if FVM_HAS_DIRICHLET
-      // Dirichlet rows keep their pattern but store explicit zeros off the diagonal
-      if (s_dir[r]) aO = 0.0;
+        // Dirichlet rows keep their pattern but store explicit zeros off the diagonal
+        if (dir) aO = 0.0;
+#if FVM_STAGE_OUT
+        out[s] = aO;
+#else
+        a.data[d.s0 + s] = aO;
 #endif
-      a.data[d.s0 + s] = aO;
-#endif
-    }
-    fvm_consumer_sync();
-
-    // ---- 4. row-parallel fold: diagonal slot, rhs / F, vertex term, Dirichlet
-    for (int r = ct; r < d.nr; r += FVM_NCT) {
-      const int b = s_rp[r] - d.s0;
-      const int e = s_rp[r + 1] - d.s0;
-      double sD = 0.0, sC = 0.0;
-      for (int s = b; s < e; ++s) {
-#if FVM_MODE != FVM_MODE_RESIDUAL
-        sD += pd[s];
-#endif
-#if FVM_MODE != FVM_MODE_JACOBIAN
-        sC += pc[s];
 #endif
       }
-      double x0 = 0.0, x1 = 0.0, x2 = 0.0, uu = 0.0, cvv = 0.0;
-#if FVM_VERT_USES_X
-      x0 = s_xy[r * FVM_DIM];
-      x1 = s_xy[r * FVM_DIM + 1];
-#if FVM_DIM == 3
-      x2 = s_xy[r * FVM_DIM + 2];
+#if FVM_GROUP > 1
+      // join the lanes of the group: fixed xor tree (deterministic)
+#pragma unroll
+      for (int w = FVM_GROUP / 2; w > 0; w >>= 1) {
+        sD += __shfl_xor_sync(0xffffffffu, sD, w);
+        sC += __shfl_xor_sync(0xffffffffu, sC, w);
+        ds = max(ds, __shfl_xor_sync(0xffffffffu, ds, w));
+      }
 #endif
-#endif
-#if FVM_VERT_USES_U
-      uu = s_u[r];
-#endif
+      if (live && gl == 0) {
+        double x2 = x02, cvv = 0.0;
 #if FVM_STAGE_CV
-      cvv = s_cv[r];
+        cvv = s_cv[g];
 #endif
 #if FVM_HAS_VERTEX
-      {
-        unsigned vm = 0xffu;
+        {
+          unsigned vm = 0xffu;
 #if FVM_VERT_MASKED
-        vm = s_vm[r];
+          vm = s_vm[g];
 #endif
-        double VL = 0.0, VC = 0.0;
-        fvm_vertex(uu, cvv, x0, x1, x2, vm, VL, VC);
-        sD += VL;
-        sC += VC;
-      }
+          double VL = 0.0, VC = 0.0;
+          fvm_vertex(u0, cvv, x00, x01, x2, vm, VL, VC);
+          sD += VL;
+          sC += VC;
+        }
 #endif
 #if FVM_MODE == FVM_MODE_LINEAR
-      double out_vec = -sC;  // rhs = -(sum of affine parts)
+        double out_vec = -sC;  // rhs = -(sum of affine parts)
 #else
-      double out_vec = sC;
+        double out_vec = sC;
 #endif
 #if FVM_HAS_DIRICHLET
-      {
-        const int id = s_dir[r];
-        if (id) {
+        if (dir) {
           double dc = 0.0, dv = 0.0;
-          fvm_dirichlet(id, uu, x0, x1, x2, dc, dv);
+          fvm_dirichlet(dir, u0, x00, x01, x2, dc, dv);
           sD = dc;       // row := coeff * e_row
           out_vec = dv;  // rhs := -affine (linear) / F := condition(u) (residual)
         }
-      }
 #endif
 #if FVM_MODE != FVM_MODE_RESIDUAL
-      a.data[d.s0 + dpos[r]] = sD;
+#if FVM_STAGE_OUT
+        out[ds] = sD;
+#else
+        a.data[d.s0 + ds] = sD;
+#endif
 #endif
 #if FVM_MODE != FVM_MODE_JACOBIAN
-      a.vec[d.r0 + r] = out_vec;
+        a.vec[d.r0 + g] = out_vec;
 #endif
+      }
     }
     // ---- release the stage to the producer (all lanes of this warp are done)
     __syncwarp();
     if ((threadIdx.x & 31) == 0) fvm_mbar_arrive(empty + st);
+#if FVM_STAGE_OUT
+    // ---- coalesced copy-out of the tile's CSR values
+    fvm_consumer_sync();
+    for (int s = ct; s < d.nsl; s += FVM_NCT) a.data[d.s0 + s] = out[s];
+#endif
   }
 }

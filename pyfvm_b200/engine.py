@@ -52,6 +52,7 @@ class KernelOpts(ctypes.Structure):
         ("consumer_warps", c_int32),
         ("stages", c_int32),
         ("ctas_per_sm", c_int32),
+        ("group", c_int32),
     ]
 
 
@@ -234,6 +235,7 @@ class Engine:
                 consumer_warps=functors.consumer_warps,
                 stages=functors.stages,
                 ctas_per_sm=functors.ctas_per_sm,
+                group=functors.group,
             )
             self._ck(
                 self.lib.fvm_kernel_create(

@@ -85,7 +85,9 @@ class _DeviceProblem:
             if kind == "linear"
             else [codegen.MODE_RESIDUAL, codegen.MODE_JACOBIAN]
         )
-        self.functors = {m: codegen.generate(lowered, m, ebits, vbits) for m in modes}
+        cell_dim = numpy.asarray(mesh.idx_hierarchy).ndim - 1  # (2,3,c): 2, (2,3,4,c): 3
+        tune = codegen.tuning(cell_dim)
+        self.functors = {m: codegen.generate(lowered, m, ebits, vbits, tune) for m in modes}
         need_el = any(f.uses_el for f in self.functors.values())
         # row_range = (first owned vertex, owned rows): row-partitioned multi-GPU runs
         self.dmesh = device_mesh(
