@@ -279,7 +279,7 @@ def run_ours(args):
             "l2": "inputs larger than L2 (no flush needed)"
             if alg > 4 * 126e6
             else "working set may fit in L2",
-            "tile_quantum": 3072,
+            "tile_quantum": int(os.environ.get("FVM_TILE_QUANTUM", "2432")),
         },
         "gpu_launches": launches,
         "clocks": clocks,

@@ -26,7 +26,7 @@ def tuning(cell_dim=2):
     (triangles: 1, tetrahedra: 8) because it shapes the floating-point fold of a
     row: the same mesh must fold the same way on one GPU and on many."""
     return {
-        "group": int(os.environ.get("FVM_GROUP", "1" if cell_dim == 2 else "8")),
+        "group": int(os.environ.get("FVM_GROUP", "2" if cell_dim == 2 else "8")),
         "consumer_warps": int(os.environ.get("FVM_CONSUMER_WARPS", "8")),
         "stages": int(os.environ.get("FVM_STAGES", "2")),
         "ctas_per_sm": int(os.environ.get("FVM_CTAS_PER_SM", "0")),
@@ -74,10 +74,13 @@ def _ccode(e):
     return _printer.doprint(sympy.sympify(e))
 
 
-def _emit_block(lines, targets, exprs, indent="    "):
-    """``target += expr`` statements for one term, sharing subexpressions.
+def _emit_block(lines, targets, exprs, indent="    ", assigned=None):
+    """``target (+)= expr`` statements for one term, sharing subexpressions.
     cse temporaries are named ``t<i>`` so they cannot collide with the edge
-    endpoint symbols ``x0_k``/``x1_k``."""
+    endpoint symbols ``x0_k``/``x1_k``.  ``assigned``: set of
+    targets already written; the first unconditional write of a target is a
+    plain assignment (the caller zero-initialises, ``0.0 + x`` is not free in
+    fp64)."""
     live = [(t, sympy.sympify(e)) for t, e in zip(targets, exprs) if t is not None]
     live = [(t, e) for t, e in live if e != 0]
     if not live:
@@ -89,13 +92,20 @@ def _emit_block(lines, targets, exprs, indent="    "):
     for sym, sub in repl:
         lines.append(f"{indent}  const double {sym} = {_ccode(sub)};")
     for (t, _), e in zip(live, red):
-        lines.append(f"{indent}  {t} += {_ccode(e)};")
+        op = "+="
+        if assigned is not None and t not in assigned:
+            op = "="
+            assigned.add(t)
+        lines.append(f"{indent}  {t} {op} {_ccode(e)};")
     lines.append(indent + "}")
 
 
-def _emit_masked(lines, bit, targets, exprs):
+def _emit_masked(lines, bit, targets, exprs, assigned):
     block = []
-    _emit_block(block, targets, exprs, indent="  ")
+    # a subdomain-restricted term is conditional: it must accumulate
+    _emit_block(block, targets, exprs, indent="  ", assigned=assigned if bit is None else None)
+    if bit is not None:
+        assigned.update(t for t in targets if t is not None)
     if block and bit is not None:
         lines.append(f"  if (mask & {1 << bit}u)")
     lines.extend(block)
@@ -191,8 +201,6 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         raise ValueError(f"undefined functions cannot be lowered to device code: {sorted(bad)}")
 
     L = [f"// generated by pyfvm_b200.codegen (mode {mode}); do not edit"]
-    if os.environ.get("FVM_DEBUG_SKIP_COMPUTE"):
-        L.append("#define FVM_DEBUG_SKIP_COMPUTE 1")
     L += [f"#define {k} {v}" for k, v in defs.items()]
     L.append("")
     L.append(
@@ -202,8 +210,9 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         "    const double edge_ce_ratio, const double edge_length, const unsigned mask,\n"
         "    double& D, double& O, double& C) {"
     )
-    for ex, bit in zip(edge_exprs, edge_bits):
-        _emit_masked(L, bit, ["D", "O", "C"], ex)
+    done = set()
+    for ex, bit in sorted(zip(edge_exprs, edge_bits), key=lambda eb: eb[1] is not None):
+        _emit_masked(L, bit, ["D", "O", "C"], ex, done)
     L.append("}")
     L.append("")
     L.append(
@@ -211,8 +220,9 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         "    const double x_0, const double x_1, const double x_2, const unsigned mask,\n"
         "    double& L, double& C) {"
     )
-    for ex, bit in zip(vert_exprs, vert_bits):
-        _emit_masked(L, bit, ["L", "C"], ex)
+    done = set()
+    for ex, bit in sorted(zip(vert_exprs, vert_bits), key=lambda eb: eb[1] is not None):
+        _emit_masked(L, bit, ["L", "C"], ex, done)
     L.append("}")
     L.append("")
     L.append(
@@ -224,7 +234,7 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         L.append("  switch (id) {")
         for k, ex in enumerate(dir_exprs):
             L.append(f"  case {k + 1}:")
-            _emit_block(L, ["coeff", "val"], ex, indent="    ")
+            _emit_block(L, ["coeff", "val"], ex, indent="    ", assigned=set())
             L.append("    break;")
         L.append("  default: break;")
         L.append("  }")

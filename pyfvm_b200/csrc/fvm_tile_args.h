@@ -7,34 +7,48 @@
 // and CSR slots are contiguous in HBM:
 //   half-edges [h0, h0+nhe) -> he_ce / he_el / he_mask streams
 //   slots      [s0, s0+nsl) -> colidx / slot_off / data
-//   vertices   [row_base+r0, +nr) -> coords / cv / u / dir_id / vmask slices
-struct FvmTileDesc {  // 32 bytes, one per tile
+//   vertices   [row_base+r0, +nr) -> cv / dir_id / vmask slices
+// Per-vertex data that slots GATHER (coordinates, u) is staged as a tile-local
+// table: the tile's own vertices (from the even vertex at or below the first
+// one), then up to two "halo" ranges holding the columns below / above the
+// tile (lo / hi).  slot_meta carries each slot's index into that table, so
+// the math warps never issue a global load.  Ranges start at even vertices and
+// have even length: every bulk copy is 16-byte aligned for 8-byte elements.
+struct FvmTileDesc {  // 64 bytes, one per tile
   long long h0;
   int r0, nr;
   int s0, nsl;
-  int nhe, pad;
+  int nhe;
+  int own_start, own_count;  // vertices [own_start, +own_count) = rows of the tile (+ alignment)
+  int lo_start, lo_count;    // halo below the tile (count 0: not covered)
+  int hi_start, hi_count;    // halo above the tile
+  int pad[3];
 };
 
+#define FVM_XLOC_NONE 0xffffu  // slot_meta high half: column not in the tile's table
+
 // Dynamic shared-memory carve-up of one CTA, identical on host and device:
-//   [full/empty mbarriers][stage 0][stage 1]...[out 0][out 1]
+//   [full/empty mbarriers][stage 0][stage 1]...
 // The stream offsets (desc .. vmask) are relative to the start of a stage.
 // Every staged stream gets 16 spare bytes: its bulk copy starts at the 16B
 // boundary below the first element and is rounded up to 16B.
 struct FvmSmemLayout {
   unsigned bar, stage0, stage_bytes;
-  unsigned desc, ce, el, mask, col, off, rowptr, cv, xy, u, dir, vmask;  // within a stage
-  unsigned out, out_bytes, total;  // double-buffered CSR-value staging (row group < 4)
+  // within a stage (out: CSR-value staging for coalesced stores, row group < 4)
+  unsigned desc, ce, el, mask, meta, rowptr, cv, xy, u, dir, vmask, out;
+  unsigned total;
 };
 
 struct FvmTileArgs {
   const FvmTileDesc* tiles;        // [ntiles]
   const int* indptr;               // [nrows+1] CSR row pointer
   const int* colidx;               // [nnz] column (local vertex id) of every slot
-  const unsigned short* slot_off;  // [nnz] first half-edge of the slot, relative to its tile
+  const unsigned* slot_meta;       // [nnz] low 16: first half-edge of the slot relative to its
+                                   //       tile; high 16: index into the tile's vertex table
   const double* he_ce;             // [H] edge_ce_ratio in half-edge order
   const double* he_el;             // [H] edge_length in half-edge order (or null)
   const unsigned char* he_mask;    // [H] edge-term subdomain bits (or null)
-  const double* coords;            // [nverts*dim] vertex coordinates
+  const double* coords;            // [nverts*xs] vertex coordinates, xs = 2 (dim 2) or 4 (dim 3)
   const double* cv;                // [nverts] control volumes
   const unsigned char* vmask;      // [nverts] vertex-term subdomain bits (or null)
   const unsigned char* dir_id;     // [nverts] 0 = free, k = Dirichlet term k-1 wins (or null)
@@ -46,6 +60,7 @@ struct FvmTileArgs {
   int max_he;                      // largest tile: half-edges
   int max_slots;                   //               slots
   int max_rows;                    //               rows
+  int max_xtab;                    //               vertex-table entries (own + halos)
   struct FvmSmemLayout L;          // shared-memory carve-up (host: fvm_smem_layout)
 };
 
@@ -70,30 +85,31 @@ struct FvmTileArgs {
 
 FVM_HD inline unsigned fvm_round16(unsigned x) { return (x + 15u) & ~15u; }
 
-FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_rows, int dim,
-                                            unsigned flags, int mode, int stages, int group) {
+FVM_HD inline unsigned fvm_coord_stride(int dim) { return dim == 2 ? 2u : 4u; }
+
+FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_rows, int max_xtab,
+                                            int dim, unsigned flags, int mode, int stages,
+                                            int group) {
   FvmSmemLayout L;
   const unsigned he = (unsigned)max_he, sl = (unsigned)max_slots, nr = (unsigned)max_rows;
   unsigned o = 0;  // within a stage
-  L.desc = o;   o += 32;
+  const unsigned xt = (unsigned)max_xtab;
+  L.desc = o;   o += 64;
   L.ce = o;     o += fvm_round16(he * 8u) + 16u;
   L.el = o;     o += (flags & FVM_F_EDGE_EL) ? fvm_round16(he * 8u) + 16u : 0u;
   L.mask = o;   o += (flags & FVM_F_EDGE_MASK) ? fvm_round16(he) + 16u : 0u;
-  L.col = o;    o += fvm_round16(sl * 4u) + 16u;
-  L.off = o;    o += fvm_round16(sl * 2u) + 16u;
+  L.meta = o;   o += fvm_round16(sl * 4u) + 16u;
   L.rowptr = o; o += fvm_round16((nr + 1u) * 4u) + 16u;
   L.cv = o;     o += (flags & FVM_F_CV) ? fvm_round16(nr * 8u) + 16u : 0u;
-  L.xy = o;     o += (flags & FVM_F_X) ? fvm_round16(nr * 8u * (unsigned)dim) + 16u : 0u;
-  L.u = o;      o += (flags & FVM_F_U) ? fvm_round16(nr * 8u) + 16u : 0u;
+  L.xy = o;     o += (flags & FVM_F_X) ? fvm_round16(xt * 8u * fvm_coord_stride(dim)) : 0u;
+  L.u = o;      o += (flags & FVM_F_U) ? fvm_round16(xt * 8u) : 0u;
   L.dir = o;    o += (flags & FVM_F_DIR) ? fvm_round16(nr) + 16u : 0u;
   L.vmask = o;  o += (flags & FVM_F_VMASK) ? fvm_round16(nr) + 16u : 0u;
+  L.out = o;    o += (group < 4 && mode != FVM_MODE_RESIDUAL) ? fvm_round16(sl * 8u) : 0u;
   L.stage_bytes = o;
   L.bar = 0;
   L.stage0 = fvm_round16(16u * (unsigned)stages);  // 2 x 8B mbarriers per stage
   o = L.stage0 + L.stage_bytes * (unsigned)stages;
-  L.out = o;
-  L.out_bytes = (group < 4 && mode != FVM_MODE_RESIDUAL) ? fvm_round16(sl * 8u) : 0u;
-  o += 2u * L.out_bytes;
   L.total = o;
   return L;
 }

@@ -21,13 +21,16 @@
 //   producer warp  : reads the 32-byte tile descriptor and issues TMA bulk copies
 //                    (cp.async.bulk, SASS UBLKCP) of every contiguous stream the
 //                    tile needs -- ce_ratio / edge_length / mask per half-edge,
-//                    column + offset per slot, row pointer / coords / cv / u /
-//                    Dirichlet id per row -- one or more tiles ahead of the math;
+//                    offset + table index per slot, row pointer / cv / Dirichlet id
+//                    per row, and the tile-local vertex table (own rows + the
+//                    halo ranges holding the neighbour columns) of coordinates
+//                    and u -- one or more tiles ahead of the math;
 //   consumer warps : a group of FVM_GROUP lanes owns one matrix row: lane j folds
 //                    the row's CSR slots j, j+G, ... -- each slot's contributions in
 //                    half-edge order out of shared memory (deterministic,
-//                    atomic-free), gathering x/u only for columns outside the
-//                    tile -- and keeps the row's diagonal / rhs sums in registers;
+//                    atomic-free), reading x/u of its column from the staged vertex
+//                    table (a global gather only where a tile's halo is not
+//                    compact) -- and keeps the row's diagonal / rhs sums in registers;
 //                    a fixed xor-shuffle tree joins the lanes; lane 0 adds the
 //                    vertex term and applies the Dirichlet row replacement in the
 //                    same pass.  CSR values leave through a double-buffered
@@ -49,6 +52,7 @@
 #define FVM_VERT_MASKED ((FVM_FLAGS & FVM_F_VMASK) != 0)
 #define FVM_HAS_DIRICHLET ((FVM_FLAGS & FVM_F_DIR) != 0)
 
+#define FVM_XS (FVM_DIM == 2 ? 2 : 4)       // doubles per vertex in the coordinate arrays
 #define FVM_NCT (32 * FVM_CONSUMER_WARPS)  // consumer threads
 #define FVM_STAGE_OUT (FVM_GROUP < 4 && FVM_MODE != FVM_MODE_RESIDUAL)
 #define FVM_THREADS (FVM_NCT + 32)         // + one producer warp
@@ -88,43 +92,20 @@ __device__ __forceinline__ void fvm_bulk_g2s(void* dst, const void* src, unsigne
       : "memory");
 }
 
+// try_wait suspends the warp in hardware for up to the time hint (ns) before it
+// reports failure, so a waiting warp does not burn issue slots
 __device__ __forceinline__ void fvm_mbar_wait(void* bar, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "FVM_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra FVM_DONE;\n"
       "bra FVM_WAIT;\n"
       "FVM_DONE:\n"
       "}\n" ::"r"(fvm_smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
-}
-
-// same, for the producer: back off between polls so the spin does not take
-// issue slots from the consumer warps of this SM sub-partition
-__device__ __forceinline__ void fvm_mbar_wait_backoff(void* bar, unsigned parity) {
-  const unsigned addr = fvm_smem_u32(bar);
-  for (;;) {
-    unsigned done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    __nanosleep(256);
-  }
-}
-
-// barrier among the consumer warps only (the producer warp never joins)
-__device__ __forceinline__ void fvm_consumer_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(FVM_NCT) : "memory");
 }
 
 // One staged stream: `nbytes` bytes at global address g (any alignment) land in
@@ -155,10 +136,11 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
   *(FvmTileDesc*)(stage + L.desc) = d;
   unsigned total = 0;
   const FvmStage g_ce = fvm_stage(a.he_ce + d.h0, (unsigned)d.nhe * 8u);
-  const FvmStage g_col = fvm_stage(a.colidx + d.s0, (unsigned)d.nsl * 4u);
-  const FvmStage g_off = fvm_stage(a.slot_off + d.s0, (unsigned)d.nsl * 2u);
+  const FvmStage g_meta = fvm_stage(a.slot_meta + d.s0, (unsigned)d.nsl * 4u);
   const FvmStage g_rp = fvm_stage(a.indptr + d.r0, (unsigned)(d.nr + 1) * 4u);
-  total += g_ce.bytes + g_col.bytes + g_off.bytes + g_rp.bytes;
+  total += g_ce.bytes + g_meta.bytes + g_rp.bytes;
+  // vertex table: own rows, halo below, halo above (even starts, even counts)
+  const unsigned n_tab = (unsigned)(d.own_count + d.lo_count + d.hi_count);
 #if FVM_EDGE_USES_EL
   const FvmStage g_el = fvm_stage(a.he_el + d.h0, (unsigned)d.nhe * 8u);
   total += g_el.bytes;
@@ -172,12 +154,10 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
   total += g_cv.bytes;
 #endif
 #if FVM_STAGE_X
-  const FvmStage g_xy = fvm_stage(a.coords + (size_t)v0 * FVM_DIM, (unsigned)d.nr * 8u * FVM_DIM);
-  total += g_xy.bytes;
+  total += n_tab * 8u * FVM_XS;
 #endif
 #if FVM_STAGE_U
-  const FvmStage g_u = fvm_stage(a.u + v0, (unsigned)d.nr * 8u);
-  total += g_u.bytes;
+  total += n_tab * 8u;
 #endif
 #if FVM_HAS_DIRICHLET
   const FvmStage g_dir = fvm_stage(a.dir_id + v0, (unsigned)d.nr);
@@ -189,8 +169,7 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
 #endif
   fvm_mbar_expect_tx(full, total);  // release: the descriptor store above is visible
   if (g_ce.bytes) fvm_bulk_g2s(stage + L.ce, g_ce.src, g_ce.bytes, full);
-  if (g_col.bytes) fvm_bulk_g2s(stage + L.col, g_col.src, g_col.bytes, full);
-  if (g_off.bytes) fvm_bulk_g2s(stage + L.off, g_off.src, g_off.bytes, full);
+  if (g_meta.bytes) fvm_bulk_g2s(stage + L.meta, g_meta.src, g_meta.bytes, full);
   fvm_bulk_g2s(stage + L.rowptr, g_rp.src, g_rp.bytes, full);
 #if FVM_EDGE_USES_EL
   if (g_el.bytes) fvm_bulk_g2s(stage + L.el, g_el.src, g_el.bytes, full);
@@ -202,10 +181,28 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
   if (g_cv.bytes) fvm_bulk_g2s(stage + L.cv, g_cv.src, g_cv.bytes, full);
 #endif
 #if FVM_STAGE_X
-  if (g_xy.bytes) fvm_bulk_g2s(stage + L.xy, g_xy.src, g_xy.bytes, full);
+  {
+    unsigned char* dst = stage + L.xy;
+    const unsigned vb = 8u * FVM_XS;  // bytes per vertex
+    if (d.own_count)
+      fvm_bulk_g2s(dst, a.coords + (size_t)d.own_start * FVM_XS, (unsigned)d.own_count * vb, full);
+    dst += (unsigned)d.own_count * vb;
+    if (d.lo_count)
+      fvm_bulk_g2s(dst, a.coords + (size_t)d.lo_start * FVM_XS, (unsigned)d.lo_count * vb, full);
+    dst += (unsigned)d.lo_count * vb;
+    if (d.hi_count)
+      fvm_bulk_g2s(dst, a.coords + (size_t)d.hi_start * FVM_XS, (unsigned)d.hi_count * vb, full);
+  }
 #endif
 #if FVM_STAGE_U
-  if (g_u.bytes) fvm_bulk_g2s(stage + L.u, g_u.src, g_u.bytes, full);
+  {
+    unsigned char* dst = stage + L.u;
+    if (d.own_count) fvm_bulk_g2s(dst, a.u + d.own_start, (unsigned)d.own_count * 8u, full);
+    dst += (unsigned)d.own_count * 8u;
+    if (d.lo_count) fvm_bulk_g2s(dst, a.u + d.lo_start, (unsigned)d.lo_count * 8u, full);
+    dst += (unsigned)d.lo_count * 8u;
+    if (d.hi_count) fvm_bulk_g2s(dst, a.u + d.hi_start, (unsigned)d.hi_count * 8u, full);
+  }
 #endif
 #if FVM_HAS_DIRICHLET
   if (g_dir.bytes) fvm_bulk_g2s(stage + L.dir, g_dir.src, g_dir.bytes, full);
@@ -215,11 +212,36 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
 #endif
 }
 
+// Columns a tile's halo ranges do not cover (irregular numbering) are gathered
+// from global memory.  Kept out of line so the hot loop carries a branch, not
+// the predicated body.
+__device__ __noinline__ double4 fvm_gather_column(const int* colidx, const double* coords,
+                                                  const double* u, int slot) {
+  double4 r = make_double4(0.0, 0.0, 0.0, 0.0);  // x1_0, x1_1, x1_2, u1
+  const int col = __ldg(colidx + slot);
+#if FVM_EDGE_USES_X
+  const double* p1 = coords + (size_t)col * FVM_XS;
+  const double2 q = __ldg((const double2*)p1);
+  r.x = q.x;
+  r.y = q.y;
+#if FVM_DIM == 3
+  r.z = __ldg(p1 + 2);
+#endif
+#endif
+#if FVM_EDGE_USES_U
+  r.w = __ldg(u + col);
+#endif
+  return r;
+}
+
 __device__ __forceinline__ FvmTileDesc fvm_load_desc(const FvmTileDesc* g) {
   FvmTileDesc d;
   const int4 d0 = __ldg((const int4*)g), d1 = __ldg((const int4*)g + 1);
+  const int4 d2 = __ldg((const int4*)g + 2), d3 = __ldg((const int4*)g + 3);
   ((int4*)&d)[0] = d0;
   ((int4*)&d)[1] = d1;
+  ((int4*)&d)[2] = d2;
+  ((int4*)&d)[3] = d3;
   return d;
 }
 
@@ -249,7 +271,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
           const int tn = t + gridDim.x;
           FvmTileDesc dn = d;
           if (tn < a.ntiles) dn = fvm_load_desc(a.tiles + tn);  // next descriptor in flight
-          if (it >= FVM_STAGES) fvm_mbar_wait_backoff(empty + st, ((it / FVM_STAGES) - 1) & 1);
+          if (it >= FVM_STAGES) fvm_mbar_wait(empty + st, ((it / FVM_STAGES) - 1) & 1);
           fvm_produce(a, L, sm + L.stage0 + st * L.stage_bytes, full + st, d);
           d = dn;
           t = tn;
@@ -274,9 +296,8 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
     const int v0 = a.row_base + d.r0;  // first vertex of the tile
 
     const double* s_ce = (const double*)(stage + L.ce + fvm_shift(a.he_ce + d.h0));
-    const int* s_col = (const int*)(stage + L.col + fvm_shift(a.colidx + d.s0));
-    const unsigned short* s_off =
-        (const unsigned short*)(stage + L.off + fvm_shift(a.slot_off + d.s0));
+    const unsigned* s_meta = (const unsigned*)(stage + L.meta + fvm_shift(a.slot_meta + d.s0));
+    const int xoff = v0 - d.own_start;  // table index of the tile's first row (0 or 1)
     const int* s_rp = (const int*)(stage + L.rowptr + fvm_shift(a.indptr + d.r0));
 #if FVM_EDGE_USES_EL
     const double* s_el = (const double*)(stage + L.el + fvm_shift(a.he_el + d.h0));
@@ -288,10 +309,10 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
     const double* s_cv = (const double*)(stage + L.cv + fvm_shift(a.cv + v0));
 #endif
 #if FVM_STAGE_X
-    const double* s_xy = (const double*)(stage + L.xy + fvm_shift(a.coords + (size_t)v0 * FVM_DIM));
+    const double* s_xy = (const double*)(stage + L.xy);
 #endif
 #if FVM_STAGE_U
-    const double* s_u = (const double*)(stage + L.u + fvm_shift(a.u + v0));
+    const double* s_u = (const double*)(stage + L.u);
 #endif
 #if FVM_HAS_DIRICHLET
     const unsigned char* s_dir = stage + L.dir + fvm_shift(a.dir_id + v0);
@@ -300,12 +321,9 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
     const unsigned char* s_vm = stage + L.vmask + fvm_shift(a.vmask + v0);
 #endif
 #if FVM_STAGE_OUT
-    double* out = (double*)(sm + L.out + (unsigned)(it & 1) * L.out_bytes);
+    double* out = (double*)(stage + L.out);  // lives and dies with the stage
 #endif
 
-#ifdef FVM_DEBUG_SKIP_COMPUTE  // experiment: stream the tiles, do no math (results are garbage)
-    if (false)
-#endif
     for (int g0 = 0; g0 < d.nr; g0 += NG) {  // trip count uniform over the consumer warps
       const int g = g0 + gi;                 // row of this lane group (tile-local)
       const bool live = g < d.nr;
@@ -318,18 +336,17 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
       int dir = 0;
       if (live) {
 #if FVM_STAGE_X
-#if FVM_DIM == 2
-        const double2 q0 = *(const double2*)(s_xy + 2 * g);
-        x00 = q0.x;
-        x01 = q0.y;
-#else
-        x00 = s_xy[3 * g];
-        x01 = s_xy[3 * g + 1];
-        x02 = s_xy[3 * g + 2];
+        {
+          const double2 q0 = *(const double2*)(s_xy + FVM_XS * (xoff + g));
+          x00 = q0.x;
+          x01 = q0.y;
+#if FVM_DIM == 3
+          x02 = s_xy[FVM_XS * (xoff + g) + 2];
 #endif
+        }
 #endif
 #if FVM_STAGE_U
-        u0 = s_u[g];
+        u0 = s_u[xoff + g];
 #endif
 #if FVM_HAS_DIRICHLET
         dir = s_dir[g];
@@ -338,41 +355,35 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
       double sD = 0.0, sC = 0.0;  // this lane's share of the row's diagonal / rhs sums
       int ds = -1;                // the row's diagonal slot, seen by exactly one lane
       for (int s = b + gl; s < e; s += FVM_GROUP) {
-        const int lo = s_off[s];
-        const int hi = (s + 1 < d.nsl) ? (int)s_off[s + 1] : d.nhe;
+        const unsigned meta = s_meta[s];
+        const int lo = (int)(meta & 0xffffu);
+        const int hi = (s + 1 < d.nsl) ? (int)(s_meta[s + 1] & 0xffffu) : d.nhe;
         if (lo == hi) {  // the diagonal slot owns no half-edge of its own
           ds = s;
           continue;
         }
-        const int col = s_col[s];
-        const unsigned cl = (unsigned)(col - v0);  // tile-local column, if inside
+        const unsigned xl = meta >> 16;  // index of the slot's column in the vertex table
         double x10 = 0.0, x11 = 0.0, x12 = 0.0, u1 = 0.0;
+#if FVM_EDGE_USES_X || FVM_EDGE_USES_U
+        if (xl != FVM_XLOC_NONE) {
 #if FVM_EDGE_USES_X
-        if (cl < (unsigned)d.nr) {
-#if FVM_DIM == 2
-          const double2 q = *(const double2*)(s_xy + 2 * cl);
+          const double2 q = *(const double2*)(s_xy + FVM_XS * xl);
           x10 = q.x;
           x11 = q.y;
-#else
-          x10 = s_xy[3 * cl];
-          x11 = s_xy[3 * cl + 1];
-          x12 = s_xy[3 * cl + 2];
+#if FVM_DIM == 3
+          x12 = s_xy[FVM_XS * xl + 2];
 #endif
-        } else {
-          const double* p1 = a.coords + (size_t)col * FVM_DIM;
-#if FVM_DIM == 2
-          const double2 q = __ldg((const double2*)p1);
-          x10 = q.x;
-          x11 = q.y;
-#else
-          x10 = __ldg(p1);
-          x11 = __ldg(p1 + 1);
-          x12 = __ldg(p1 + 2);
-#endif
-        }
 #endif
 #if FVM_EDGE_USES_U
-        u1 = (cl < (unsigned)d.nr) ? s_u[cl] : __ldg(a.u + col);
+          u1 = s_u[xl];
+#endif
+        } else {  // column outside the staged halo ranges: gather it (cold path)
+          const double4 gq = fvm_gather_column(a.colidx, a.coords, a.u, d.s0 + s);
+          x10 = gq.x;
+          x11 = gq.y;
+          x12 = gq.z;
+          u1 = gq.w;
+        }
 #endif
         double aD = 0.0, aO = 0.0, aC = 0.0;
 #if FVM_EDGE_FACTORED
@@ -465,14 +476,23 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
         a.vec[d.r0 + g] = out_vec;
 #endif
       }
+#if FVM_STAGE_OUT
+      {
+        // coalesced copy-out of the CSR values of this warp's rows: they are
+        // consecutive, so are their slots; no other warp touches this range
+        constexpr int RPW = 32 / FVM_GROUP;  // rows per warp and chunk
+        const int gw = g0 + (ct >> 5) * RPW;
+        if (gw < d.nr) {
+          const int ge = min(gw + RPW, d.nr);
+          const int sbeg = s_rp[gw] - d.s0, send = s_rp[ge] - d.s0;
+          __syncwarp();
+          for (int s = sbeg + (ct & 31); s < send; s += 32) a.data[d.s0 + s] = out[s];
+        }
+      }
+#endif
     }
     // ---- release the stage to the producer (all lanes of this warp are done)
     __syncwarp();
     if ((threadIdx.x & 31) == 0) fvm_mbar_arrive(empty + st);
-#if FVM_STAGE_OUT
-    // ---- coalesced copy-out of the tile's CSR values
-    fvm_consumer_sync();
-    for (int s = ct; s < d.nsl; s += FVM_NCT) a.data[d.s0 + s] = out[s];
-#endif
   }
 }
