@@ -104,6 +104,14 @@ int fvm_mesh_destroy(fvm_mesh* mesh);
  * on-device pattern build */
 int fvm_mesh_info(fvm_mesh* mesh, int64_t* nnz, int64_t* n_halfedges, int32_t* n_tiles,
                   float* build_ms);
+/* layout diagnostics, out[0..n): largest tile (half-edges, slots, rows, vertex-table
+ * entries), slots whose column lies outside the staged vertex tables (they are
+ * gathered from global memory instead), tile quantum, tiles, half-edges */
+int fvm_mesh_stats(fvm_mesh* mesh, int64_t* out, int n);
+/* copy an internal layout array to the host for inspection / tests:
+ * 0 = tile descriptors (64 B each), 1 = packed slot metadata (4 B per slot),
+ * 2 = ce_ratios in half-edge order (8 B per half-edge) */
+int fvm_mesh_debug_copy(fvm_mesh* mesh, int which, void* out, size_t bytes);
 /* CSR pattern to host: indptr[n_rows+1], indices[nnz] (local vertex ids) */
 int fvm_mesh_get_pattern(fvm_mesh* mesh, int32_t* indptr, int32_t* indices);
 /* device views of the same arrays (owned by the mesh) */

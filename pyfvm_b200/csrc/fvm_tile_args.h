@@ -9,9 +9,9 @@
 //   slots      [s0, s0+nsl) -> colidx / slot_off / data
 //   vertices   [row_base+r0, +nr) -> cv / dir_id / vmask slices
 // Per-vertex data that slots GATHER (coordinates, u) is staged as a tile-local
-// table: the tile's own vertices (from the even vertex at or below the first
-// one), then up to two "halo" ranges holding the columns below / above the
-// tile (lo / hi).  slot_meta carries each slot's index into that table, so
+// table: the tile's own vertices (plus a margin of a few vertices either side),
+// then up to two "halo" ranges holding the columns below / above the tile
+// (lo / hi).  slot_meta carries each slot's index into that table, so
 // the math warps never issue a global load.  Ranges start at even vertices and
 // have even length: every bulk copy is 16-byte aligned for 8-byte elements.
 struct FvmTileDesc {  // 64 bytes, one per tile

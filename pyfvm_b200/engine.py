@@ -79,6 +79,8 @@ SYMBOLS = {
         c_int,
         [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int32), POINTER(c_float)],
     ),
+    "fvm_mesh_stats": (c_int, [c_void_p, POINTER(c_int64), c_int]),
+    "fvm_mesh_debug_copy": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     "fvm_mesh_get_pattern": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fvm_mesh_pattern_dev": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
     "fvm_mesh_update_geometry": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
@@ -349,6 +351,32 @@ class DeviceMesh:
             ms.value,
         )
         self._pattern = None
+
+    TILE_DTYPE = numpy.dtype(
+        [("h0", "<i8"), ("r0", "<i4"), ("nr", "<i4"), ("s0", "<i4"), ("nsl", "<i4"),
+         ("nhe", "<i4"), ("own_start", "<i4"), ("own_count", "<i4"), ("lo_start", "<i4"),
+         ("lo_count", "<i4"), ("hi_start", "<i4"), ("hi_count", "<i4"), ("pad", "<i4", (3,))]
+    )
+
+    def stats(self):
+        """Layout diagnostics of the device mesh (see ``fvm_mesh_stats``)."""
+        out = (c_int64 * 8)()
+        self.eng._ck(self.eng.lib.fvm_mesh_stats(self.handle, out, 8))
+        keys = ["max_he", "max_slots", "max_rows", "max_xtab", "uncovered_slots", "quantum",
+                "tiles", "halfedges"]
+        return dict(zip(keys, [int(x) for x in out]))
+
+    def layout(self):
+        """Host copies of the device layout (tests / inspection): tile descriptors,
+        packed slot metadata, ce_ratios in half-edge order."""
+        tiles = numpy.empty(self.n_tiles, dtype=self.TILE_DTYPE)
+        meta = numpy.empty(self.nnz, dtype=numpy.uint32)
+        ce = numpy.empty(self.n_halfedges, dtype=numpy.float64)
+        for which, arr in ((0, tiles), (1, meta), (2, ce)):
+            self.eng._ck(
+                self.eng.lib.fvm_mesh_debug_copy(self.handle, which, _ptr(arr), arr.nbytes)
+            )
+        return tiles, meta, ce
 
     def pattern(self):
         """Host copy of ``(indptr, indices)`` (int32), fetched once."""

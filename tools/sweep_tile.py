@@ -54,6 +54,7 @@ def main():
     u = eng.to_device(numpy.random.default_rng(0).standard_normal(n))
     for q in ints(args.quantum):
         dm = engine.DeviceMesh(eng, mesh, need_el=False, tile_quantum=q)
+        print(dm.stats(), flush=True)
         data = eng.alloc(8 * dm.nnz)
         vec = eng.alloc(8 * n)
         groups = ints(args.group) if args.group else [8 if args.cube else 1]
