@@ -17,17 +17,16 @@ MODE_LINEAR, MODE_RESIDUAL, MODE_JACOBIAN = 0, 1, 2
 
 # FVM_F_* bits of csrc/fvm_tile_args.h (= FVM_KF_* of include/fvm_b200.h)
 F_EDGE_EL, F_EDGE_MASK, F_X, F_U, F_CV, F_VMASK, F_DIR = 1, 2, 4, 8, 16, 32, 64
+F_EDGE_D, F_EDGE_C = 128, 256
 
 
 def tuning(cell_dim=2):
     """Launch-shape knobs of the tile kernel (env overrides are for experiments).
 
-    ``group`` = lanes that share one matrix row.  It is fixed per cell type
-    (triangles: 1, tetrahedra: 8) because it shapes the floating-point fold of a
-    row: the same mesh must fold the same way on one GPU and on many."""
+    None of them changes a result bit: the fold order of a slot / row is fixed
+    by the mesh alone."""
     return {
-        "group": int(os.environ.get("FVM_GROUP", "2" if cell_dim == 2 else "8")),
-        "consumer_warps": int(os.environ.get("FVM_CONSUMER_WARPS", "8")),
+        "consumer_warps": int(os.environ.get("FVM_CONSUMER_WARPS", "4")),
         "stages": int(os.environ.get("FVM_STAGES", "2")),
         "ctas_per_sm": int(os.environ.get("FVM_CTAS_PER_SM", "0")),
         # fold the ce_ratios of a slot first and evaluate ce*g(slot) once
@@ -136,7 +135,6 @@ class Functors:
     consumer_warps: int
     stages: int
     ctas_per_sm: int
-    group: int
     factored: bool
     uses_el: bool
     uses_x: bool
@@ -170,6 +168,10 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
     flags |= F_CV if _uses(flat_v, [lo.CV]) else 0
     flags |= F_VMASK if any(b is not None for b in vert_bits) else 0
     flags |= F_DIR if lowered.dirichlet else 0
+    # which row sums the edge functor feeds in this mode (their per-slot shares
+    # are parked in shared memory between the slot pass and the row pass)
+    flags |= F_EDGE_D if any(sympy.sympify(ex[0]) != 0 for ex in edge_exprs) else 0
+    flags |= F_EDGE_C if any(sympy.sympify(ex[2]) != 0 for ex in edge_exprs) else 0
     # Every dS integrand is multiplied by edge_ce_ratio (App. A.2), so the edge
     # outputs are ce * g(x0, x1, u0, u1).  When nothing else varies per half-edge
     # (no edge_length, no subdomain bits) the kernel sums the ce_ratios of a slot
@@ -186,7 +188,6 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         "FVM_FLAGS": f"{flags}u",
         "FVM_CONSUMER_WARPS": tune["consumer_warps"],
         "FVM_STAGES": tune["stages"],
-        "FVM_GROUP": tune["group"],
         "FVM_EDGE_FACTORED": int(factored),
         "FVM_EDGE_USES_X": int(edge_x),
         "FVM_EDGE_USES_U": int(edge_u),
@@ -247,7 +248,6 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         consumer_warps=tune["consumer_warps"],
         stages=tune["stages"],
         ctas_per_sm=tune["ctas_per_sm"],
-        group=tune["group"],
         factored=factored,
         uses_el=bool(flags & F_EDGE_EL),
         uses_x=bool(flags & F_X),

@@ -14,7 +14,15 @@
 // (lo / hi).  slot_meta carries each slot's index into that table, so
 // the math warps never issue a global load.  Ranges start at even vertices and
 // have even length: every bulk copy is 16-byte aligned for 8-byte elements.
-struct FvmTileDesc {  // 64 bytes, one per tile
+//
+// slot_meta packs, per CSR slot, everything the slot-parallel pass needs:
+//   bits  0..11  first half-edge of the slot, relative to the tile   (< 4096)
+//   bits 12..19  row of the slot, relative to the tile               (< 256)
+//   bits 20..31  index of the slot's column in the tile's vertex table
+//                (FVM_XLOC_NONE: not covered -> cold global gather)
+// The pattern build sizes the tiles so that these ranges always hold.
+#define FVM_WSPLIT 16  // a tile's rows are pre-split into this many equal-work ranges
+struct FvmTileDesc {   // 96 bytes, one per tile
   long long h0;
   int r0, nr;
   int s0, nsl;
@@ -23,9 +31,20 @@ struct FvmTileDesc {  // 64 bytes, one per tile
   int lo_start, lo_count;    // halo below the tile (count 0: not covered)
   int hi_start, hi_count;    // halo above the tile
   int pad[3];
+  // wb[i] = first row (tile-local) of work range i, i in 1..15 (wb[0] = 0, range 16
+  // ends at nr): ranges hold about the same number of half-edges + slots.  A math
+  // warp owns FVM_WSPLIT / FVM_CONSUMER_WARPS consecutive ranges.
+  unsigned short wb[FVM_WSPLIT];
 };
 
-#define FVM_XLOC_NONE 0xffffu  // slot_meta high half: column not in the tile's table
+#define FVM_META_LO_BITS 12
+#define FVM_META_ROW_BITS 8
+#define FVM_META_LO_MASK 0xfffu
+#define FVM_META_ROW_MASK 0xffu
+#define FVM_XLOC_NONE 0xfffu  // slot_meta column field: column not in the tile's table
+#define FVM_TILE_MAX_HE 4095    // half-edges per tile
+#define FVM_TILE_MAX_ROWS 255   // rows per tile
+#define FVM_TILE_MAX_XTAB 4094  // vertex-table entries per tile
 
 // Dynamic shared-memory carve-up of one CTA, identical on host and device:
 //   [full/empty mbarriers][stage 0][stage 1]...
@@ -34,8 +53,9 @@ struct FvmTileDesc {  // 64 bytes, one per tile
 // boundary below the first element and is rounded up to 16B.
 struct FvmSmemLayout {
   unsigned bar, stage0, stage_bytes;
-  // within a stage (out: CSR-value staging for coalesced stores, row group < 4)
-  unsigned desc, ce, el, mask, meta, rowptr, cv, xy, u, dir, vmask, out;
+  // within a stage (accd / accc: per-slot diagonal / rhs contributions waiting for
+  // the row fold; dg: offset of the diagonal slot inside every row)
+  unsigned desc, ce, el, mask, meta, rowptr, cv, xy, u, dir, vmask, accd, accc, dg;
   unsigned total;
 };
 
@@ -43,8 +63,8 @@ struct FvmTileArgs {
   const FvmTileDesc* tiles;        // [ntiles]
   const int* indptr;               // [nrows+1] CSR row pointer
   const int* colidx;               // [nnz] column (local vertex id) of every slot
-  const unsigned* slot_meta;       // [nnz] low 16: first half-edge of the slot relative to its
-                                   //       tile; high 16: index into the tile's vertex table
+  const unsigned* slot_meta;       // [nnz] packed first half-edge | row | column location
+  const unsigned short* row_diag;  // [nrows] offset of the diagonal slot inside its row
   const double* he_ce;             // [H] edge_ce_ratio in half-edge order
   const double* he_el;             // [H] edge_length in half-edge order (or null)
   const unsigned char* he_mask;    // [H] edge-term subdomain bits (or null)
@@ -76,6 +96,8 @@ struct FvmTileArgs {
 #define FVM_F_CV 16u        // vertex functor reads control volumes
 #define FVM_F_VMASK 32u     // vertex terms carry vertex-subdomain bits
 #define FVM_F_DIR 64u       // Dirichlet conditions present
+#define FVM_F_EDGE_D 128u   // edge functor writes D (diagonal coefficient) in this mode
+#define FVM_F_EDGE_C 256u   // edge functor writes C (rhs / residual part) in this mode
 
 #ifdef __CUDACC__
 #define FVM_HD __host__ __device__
@@ -88,13 +110,12 @@ FVM_HD inline unsigned fvm_round16(unsigned x) { return (x + 15u) & ~15u; }
 FVM_HD inline unsigned fvm_coord_stride(int dim) { return dim == 2 ? 2u : 4u; }
 
 FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_rows, int max_xtab,
-                                            int dim, unsigned flags, int mode, int stages,
-                                            int group) {
+                                            int dim, unsigned flags, int mode, int stages) {
   FvmSmemLayout L;
   const unsigned he = (unsigned)max_he, sl = (unsigned)max_slots, nr = (unsigned)max_rows;
   unsigned o = 0;  // within a stage
   const unsigned xt = (unsigned)max_xtab;
-  L.desc = o;   o += 64;
+  L.desc = o;   o += 96;
   L.ce = o;     o += fvm_round16(he * 8u) + 16u;
   L.el = o;     o += (flags & FVM_F_EDGE_EL) ? fvm_round16(he * 8u) + 16u : 0u;
   L.mask = o;   o += (flags & FVM_F_EDGE_MASK) ? fvm_round16(he) + 16u : 0u;
@@ -105,7 +126,9 @@ FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_r
   L.u = o;      o += (flags & FVM_F_U) ? fvm_round16(xt * 8u) : 0u;
   L.dir = o;    o += (flags & FVM_F_DIR) ? fvm_round16(nr) + 16u : 0u;
   L.vmask = o;  o += (flags & FVM_F_VMASK) ? fvm_round16(nr) + 16u : 0u;
-  L.out = o;    o += (group < 4 && mode != FVM_MODE_RESIDUAL) ? fvm_round16(sl * 8u) : 0u;
+  L.accd = o;   o += (flags & FVM_F_EDGE_D) ? fvm_round16(sl * 8u) : 0u;
+  L.accc = o;   o += (flags & FVM_F_EDGE_C) ? fvm_round16(sl * 8u) : 0u;
+  L.dg = o;     o += (mode != FVM_MODE_RESIDUAL) ? fvm_round16(nr * 2u) + 16u : 0u;
   L.stage_bytes = o;
   L.bar = 0;
   L.stage0 = fvm_round16(16u * (unsigned)stages);  // 2 x 8B mbarriers per stage

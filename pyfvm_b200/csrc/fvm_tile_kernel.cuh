@@ -6,7 +6,7 @@
 //   FVM_MODE_JACOBIAN : jacobian.get_linear_operator(u0) values         [README:116]
 //
 // It is compiled at run time by NVRTC after a generated prelude that defines
-//   FVM_MODE, FVM_DIM, FVM_FLAGS (FVM_F_* bits), FVM_CONSUMER_WARPS, FVM_STAGES, FVM_GROUP,
+//   FVM_MODE, FVM_DIM, FVM_FLAGS (FVM_F_* bits), FVM_CONSUMER_WARPS, FVM_STAGES,
 //   FVM_EDGE_USES_X / _U, FVM_VERT_USES_X / _U, FVM_HAS_VERTEX, FVM_EDGE_FACTORED
 // and the three sympy-printed device functors
 //   fvm_edge(uk0, uk1, x0_0..2, x1_0..2, edge_ce_ratio, edge_length, mask, &D, &O, &C)
@@ -18,27 +18,32 @@
 // Persistent, warp-specialised CTAs (grid = resident CTAs of the whole GPU);
 // CTA b walks tiles b, b+grid, ... through a ring of FVM_STAGES shared-memory
 // stages guarded by full/empty mbarriers:
-//   producer warp  : reads the 32-byte tile descriptor and issues TMA bulk copies
+//   producer warp  : reads the tile descriptor and issues TMA bulk copies
 //                    (cp.async.bulk, SASS UBLKCP) of every contiguous stream the
 //                    tile needs -- ce_ratio / edge_length / mask per half-edge,
 //                    offset + table index per slot, row pointer / cv / Dirichlet id
 //                    per row, and the tile-local vertex table (own rows + the
 //                    halo ranges holding the neighbour columns) of coordinates
 //                    and u -- one or more tiles ahead of the math;
-//   consumer warps : a group of FVM_GROUP lanes owns one matrix row: lane j folds
-//                    the row's CSR slots j, j+G, ... -- each slot's contributions in
-//                    half-edge order out of shared memory (deterministic,
-//                    atomic-free), reading x/u of its column from the staged vertex
-//                    table (a global gather only where a tile's halo is not
-//                    compact) -- and keeps the row's diagonal / rhs sums in registers;
-//                    a fixed xor-shuffle tree joins the lanes; lane 0 adds the
-//                    vertex term and applies the Dirichlet row replacement in the
-//                    same pass.  CSR values leave through a double-buffered
-//                    shared staging array (FVM_GROUP < 4) so that the global
-//                    stores are coalesced, or directly (FVM_GROUP >= 4).
-// The fold order of a slot/row depends only on the row's own half-edge order and
-// FVM_GROUP (fixed per cell type), never on tile boundaries or the grid size, so
-// a row-partitioned multi-GPU run is bit-identical to the single-GPU run.
+//   consumer warps : each warp owns a run of consecutive rows of the tile (equal
+//                    work, pre-split by the pattern build) and sweeps it twice.
+//                    Pass A is SLOT-parallel: lane l takes CSR slot c+l of a
+//                    32-slot chunk, folds the slot's ce_ratios in half-edge order
+//                    out of shared memory (consecutive lanes read consecutive
+//                    addresses), evaluates the edge functor with x/u of its row and
+//                    column from the staged vertex table, stores the off-diagonal
+//                    value straight to the CSR array (consecutive lanes ->
+//                    consecutive slots: coalesced) and parks the slot's diagonal /
+//                    rhs share in shared memory.  The slot -> row map is rebuilt
+//                    per chunk from the staged row pointers with one REDUX + POPC.
+//                    Pass B is ROW-parallel: lane l folds the parked shares of row
+//                    r+l in slot order, adds the vertex term, applies the
+//                    Dirichlet row replacement in the same pass and stores the
+//                    diagonal value and the rhs / residual entry.
+// Deterministic and atomic-free: a slot is the in-order sum of its half-edges, a
+// row the in-order sum of its slots -- never a function of tile boundaries, warp
+// ranges or the grid size, so a row-partitioned multi-GPU run is bit-identical
+// to the single-GPU run.
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -52,15 +57,19 @@
 #define FVM_VERT_MASKED ((FVM_FLAGS & FVM_F_VMASK) != 0)
 #define FVM_HAS_DIRICHLET ((FVM_FLAGS & FVM_F_DIR) != 0)
 
+#define FVM_ACC_D ((FVM_FLAGS & FVM_F_EDGE_D) != 0)
+#define FVM_ACC_C ((FVM_FLAGS & FVM_F_EDGE_C) != 0)
+
 #define FVM_XS (FVM_DIM == 2 ? 2 : 4)       // doubles per vertex in the coordinate arrays
 #define FVM_NCT (32 * FVM_CONSUMER_WARPS)  // consumer threads
-#define FVM_STAGE_OUT (FVM_GROUP < 4 && FVM_MODE != FVM_MODE_RESIDUAL)
 #define FVM_THREADS (FVM_NCT + 32)         // + one producer warp
+#define FVM_FULL 0xffffffffu
 
 static_assert(!(FVM_EDGE_USES_X || FVM_VERT_USES_X) || FVM_STAGE_X, "FVM_F_X missing");
 static_assert(!(FVM_EDGE_USES_U || FVM_VERT_USES_U) || FVM_STAGE_U, "FVM_F_U missing");
-static_assert(FVM_GROUP >= 1 && FVM_GROUP <= 32 && (FVM_GROUP & (FVM_GROUP - 1)) == 0,
-              "FVM_GROUP must be a power of two");
+static_assert(FVM_WSPLIT % FVM_CONSUMER_WARPS == 0, "FVM_CONSUMER_WARPS must divide FVM_WSPLIT");
+static_assert(FVM_MODE != FVM_MODE_RESIDUAL || !FVM_ACC_D, "residual mode has no D output");
+static_assert(FVM_MODE != FVM_MODE_JACOBIAN || !FVM_ACC_C, "Jacobian mode has no C output");
 static_assert(!(FVM_EDGE_FACTORED && (FVM_EDGE_USES_EL || FVM_EDGE_MASKED)),
               "ce factoring needs a slot-invariant functor");
 
@@ -163,6 +172,10 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
   const FvmStage g_dir = fvm_stage(a.dir_id + v0, (unsigned)d.nr);
   total += g_dir.bytes;
 #endif
+#if FVM_MODE != FVM_MODE_RESIDUAL
+  const FvmStage g_dg = fvm_stage(a.row_diag + d.r0, (unsigned)d.nr * 2u);
+  total += g_dg.bytes;
+#endif
 #if FVM_VERT_MASKED
   const FvmStage g_vm = fvm_stage(a.vmask + v0, (unsigned)d.nr);
   total += g_vm.bytes;
@@ -207,6 +220,9 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
 #if FVM_HAS_DIRICHLET
   if (g_dir.bytes) fvm_bulk_g2s(stage + L.dir, g_dir.src, g_dir.bytes, full);
 #endif
+#if FVM_MODE != FVM_MODE_RESIDUAL
+  if (g_dg.bytes) fvm_bulk_g2s(stage + L.dg, g_dg.src, g_dg.bytes, full);
+#endif
 #if FVM_VERT_MASKED
   if (g_vm.bytes) fvm_bulk_g2s(stage + L.vmask, g_vm.src, g_vm.bytes, full);
 #endif
@@ -238,10 +254,13 @@ __device__ __forceinline__ FvmTileDesc fvm_load_desc(const FvmTileDesc* g) {
   FvmTileDesc d;
   const int4 d0 = __ldg((const int4*)g), d1 = __ldg((const int4*)g + 1);
   const int4 d2 = __ldg((const int4*)g + 2), d3 = __ldg((const int4*)g + 3);
+  const int4 d4 = __ldg((const int4*)g + 4), d5 = __ldg((const int4*)g + 5);
   ((int4*)&d)[0] = d0;
   ((int4*)&d)[1] = d1;
   ((int4*)&d)[2] = d2;
   ((int4*)&d)[3] = d3;
+  ((int4*)&d)[4] = d4;
+  ((int4*)&d)[5] = d5;
   return d;
 }
 
@@ -282,28 +301,31 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
   }
 
   // ========================= consumer warps ==================================
-  const int ct = threadIdx.x - 32;     // consumer thread id
-  const int gl = ct & (FVM_GROUP - 1);  // lane within the row group
-  const int gi = ct / FVM_GROUP;        // row group id
-  constexpr int NG = FVM_NCT / FVM_GROUP;
+  const int lane = threadIdx.x & 31;
+  const int cw = (threadIdx.x >> 5) - 1;  // consumer warp id
+  constexpr int WR = FVM_WSPLIT / FVM_CONSUMER_WARPS;  // work ranges per warp
 
   int it = 0;
   for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
     const int st = it % FVM_STAGES;
     unsigned char* stage = sm + L.stage0 + st * L.stage_bytes;
     fvm_mbar_wait(full + st, (it / FVM_STAGES) & 1);
-    const FvmTileDesc d = *(const FvmTileDesc*)(stage + L.desc);
-    const int v0 = a.row_base + d.r0;  // first vertex of the tile
+    const FvmTileDesc* sd = (const FvmTileDesc*)(stage + L.desc);
+    const int d_nr = sd->nr, d_s0 = sd->s0, d_nsl = sd->nsl, d_nhe = sd->nhe, d_r0 = sd->r0;
+    const int v0 = a.row_base + d_r0;  // first vertex of the tile
+    // rows [ra, rb) of the tile belong to this warp
+    const int ra = cw == 0 ? 0 : (int)sd->wb[cw * WR];
+    const int rb = cw == FVM_CONSUMER_WARPS - 1 ? d_nr : (int)sd->wb[(cw + 1) * WR];
 
-    const double* s_ce = (const double*)(stage + L.ce + fvm_shift(a.he_ce + d.h0));
-    const unsigned* s_meta = (const unsigned*)(stage + L.meta + fvm_shift(a.slot_meta + d.s0));
-    const int xoff = v0 - d.own_start;  // table index of the tile's first row (0 or 1)
-    const int* s_rp = (const int*)(stage + L.rowptr + fvm_shift(a.indptr + d.r0));
+    const double* s_ce = (const double*)(stage + L.ce + fvm_shift(a.he_ce + sd->h0));
+    const unsigned* s_meta = (const unsigned*)(stage + L.meta + fvm_shift(a.slot_meta + d_s0));
+    const int xoff = v0 - sd->own_start;  // table index of the tile's first row
+    const int* s_rp = (const int*)(stage + L.rowptr + fvm_shift(a.indptr + d_r0));
 #if FVM_EDGE_USES_EL
-    const double* s_el = (const double*)(stage + L.el + fvm_shift(a.he_el + d.h0));
+    const double* s_el = (const double*)(stage + L.el + fvm_shift(a.he_el + sd->h0));
 #endif
 #if FVM_EDGE_MASKED
-    const unsigned char* s_mask = stage + L.mask + fvm_shift(a.he_mask + d.h0);
+    const unsigned char* s_mask = stage + L.mask + fvm_shift(a.he_mask + sd->h0);
 #endif
 #if FVM_STAGE_CV
     const double* s_cv = (const double*)(stage + L.cv + fvm_shift(a.cv + v0));
@@ -320,22 +342,118 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
 #if FVM_VERT_MASKED
     const unsigned char* s_vm = stage + L.vmask + fvm_shift(a.vmask + v0);
 #endif
-#if FVM_STAGE_OUT
-    double* out = (double*)(stage + L.out);  // lives and dies with the stage
+#if FVM_ACC_D
+    double* s_accd = (double*)(stage + L.accd);  // lives and dies with the stage
+#endif
+#if FVM_ACC_C
+    double* s_accc = (double*)(stage + L.accc);
+#endif
+#if FVM_MODE != FVM_MODE_RESIDUAL
+    const unsigned short* s_dg =
+        (const unsigned short*)(stage + L.dg + fvm_shift(a.row_diag + d_r0));
 #endif
 
-    for (int g0 = 0; g0 < d.nr; g0 += NG) {  // trip count uniform over the consumer warps
-      const int g = g0 + gi;                 // row of this lane group (tile-local)
-      const bool live = g < d.nr;
-      int b = 0, e = 0;
-      if (live) {
-        b = s_rp[g] - d.s0;
-        e = s_rp[g + 1] - d.s0;
+    if (ra < rb) {
+      // ---------------- pass A: one lane per CSR slot -------------------------
+      const int sa = s_rp[ra] - d_s0, sb = s_rp[rb] - d_s0;  // this warp's slots
+#pragma unroll 1
+      for (int s = sa + lane; s < sb; s += 32) {
+        const unsigned meta = s_meta[s];
+        const int lo = (int)(meta & FVM_META_LO_MASK);
+        const int hi = (s + 1 < d_nsl) ? (int)(s_meta[s + 1] & FVM_META_LO_MASK) : d_nhe;
+        double aD = 0.0, aO = 0.0, aC = 0.0;
+        if (lo < hi) {  // the diagonal slot owns no half-edge; pass B writes it
+          const int g = (int)((meta >> FVM_META_LO_BITS) & FVM_META_ROW_MASK);  // row of the slot
+          double x00 = 0.0, x01 = 0.0, x02 = 0.0, u0 = 0.0;
+          double x10 = 0.0, x11 = 0.0, x12 = 0.0, u1 = 0.0;
+#if FVM_EDGE_USES_X
+          {
+            const double2 q0 = *(const double2*)(s_xy + FVM_XS * (xoff + g));
+            x00 = q0.x;
+            x01 = q0.y;
+#if FVM_DIM == 3
+            x02 = s_xy[FVM_XS * (xoff + g) + 2];
+#endif
+          }
+#endif
+#if FVM_EDGE_USES_U
+          u0 = s_u[xoff + g];
+#endif
+#if FVM_EDGE_USES_X || FVM_EDGE_USES_U
+          const unsigned xl = meta >> (FVM_META_LO_BITS + FVM_META_ROW_BITS);
+          if (xl != FVM_XLOC_NONE) {
+#if FVM_EDGE_USES_X
+            const double2 q = *(const double2*)(s_xy + FVM_XS * xl);
+            x10 = q.x;
+            x11 = q.y;
+#if FVM_DIM == 3
+            x12 = s_xy[FVM_XS * xl + 2];
+#endif
+#endif
+#if FVM_EDGE_USES_U
+            u1 = s_u[xl];
+#endif
+          } else {  // column outside the staged halo ranges: gather it (cold path)
+            const double4 gq = fvm_gather_column(a.colidx, a.coords, a.u, d_s0 + s);
+            x10 = gq.x;
+            x11 = gq.y;
+            x12 = gq.z;
+            u1 = gq.w;
+          }
+#endif
+#if FVM_EDGE_FACTORED
+          // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
+          double ce = s_ce[lo];
+#pragma unroll 1
+          for (int k = lo + 1; k < hi; ++k) ce += s_ce[k];
+          fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, 0.0, 0xffu, aD, aO, aC);
+#else
+#pragma unroll 1
+          for (int k = lo; k < hi; ++k) {
+            const double ce = s_ce[k];
+            double el = 0.0;
+            unsigned m = 0xffu;
+#if FVM_EDGE_USES_EL
+            el = s_el[k];
+#endif
+#if FVM_EDGE_MASKED
+            m = s_mask[k];
+#endif
+            double D = 0.0, O = 0.0, C = 0.0;
+            fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, el, m, D, O, C);
+            aD += D;
+            aO += O;
+            aC += C;
+          }
+#endif
+#if FVM_MODE != FVM_MODE_RESIDUAL
+          a.data[d_s0 + s] = aO;  // consecutive lanes, consecutive slots: coalesced
+#endif
+        }
+#if FVM_ACC_D
+        s_accd[s] = aD;
+#endif
+#if FVM_ACC_C
+        s_accc[s] = aC;
+#endif
       }
-      double x00 = 0.0, x01 = 0.0, x02 = 0.0, u0 = 0.0;
-      int dir = 0;
-      if (live) {
-#if FVM_STAGE_X
+      __syncwarp();  // the parked shares are visible to the whole warp
+
+      // ---------------- pass B: one lane per matrix row ------------------------
+      for (int g = ra + lane; g < rb; g += 32) {
+        const int b = s_rp[g] - d_s0, e = s_rp[g + 1] - d_s0;
+        double sD = 0.0, sC = 0.0;
+#pragma unroll 1
+        for (int s = b; s < e; ++s) {  // in slot order (deterministic)
+#if FVM_ACC_D
+          sD += s_accd[s];
+#endif
+#if FVM_ACC_C
+          sC += s_accc[s];
+#endif
+        }
+        double x00 = 0.0, x01 = 0.0, x02 = 0.0, u0 = 0.0, cvv = 0.0;
+#if FVM_STAGE_X && (FVM_VERT_USES_X)
         {
           const double2 q0 = *(const double2*)(s_xy + FVM_XS * (xoff + g));
           x00 = q0.x;
@@ -345,98 +463,9 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
 #endif
         }
 #endif
-#if FVM_STAGE_U
+#if FVM_STAGE_U && (FVM_VERT_USES_U)
         u0 = s_u[xoff + g];
 #endif
-#if FVM_HAS_DIRICHLET
-        dir = s_dir[g];
-#endif
-      }
-      double sD = 0.0, sC = 0.0;  // this lane's share of the row's diagonal / rhs sums
-      int ds = -1;                // the row's diagonal slot, seen by exactly one lane
-      for (int s = b + gl; s < e; s += FVM_GROUP) {
-        const unsigned meta = s_meta[s];
-        const int lo = (int)(meta & 0xffffu);
-        const int hi = (s + 1 < d.nsl) ? (int)(s_meta[s + 1] & 0xffffu) : d.nhe;
-        if (lo == hi) {  // the diagonal slot owns no half-edge of its own
-          ds = s;
-          continue;
-        }
-        const unsigned xl = meta >> 16;  // index of the slot's column in the vertex table
-        double x10 = 0.0, x11 = 0.0, x12 = 0.0, u1 = 0.0;
-#if FVM_EDGE_USES_X || FVM_EDGE_USES_U
-        if (xl != FVM_XLOC_NONE) {
-#if FVM_EDGE_USES_X
-          const double2 q = *(const double2*)(s_xy + FVM_XS * xl);
-          x10 = q.x;
-          x11 = q.y;
-#if FVM_DIM == 3
-          x12 = s_xy[FVM_XS * xl + 2];
-#endif
-#endif
-#if FVM_EDGE_USES_U
-          u1 = s_u[xl];
-#endif
-        } else {  // column outside the staged halo ranges: gather it (cold path)
-          const double4 gq = fvm_gather_column(a.colidx, a.coords, a.u, d.s0 + s);
-          x10 = gq.x;
-          x11 = gq.y;
-          x12 = gq.z;
-          u1 = gq.w;
-        }
-#endif
-        double aD = 0.0, aO = 0.0, aC = 0.0;
-#if FVM_EDGE_FACTORED
-        // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
-        double ce = s_ce[lo];
-        if (hi - lo > 1) {
-          ce += s_ce[lo + 1];
-#pragma unroll 1
-          for (int k = lo + 2; k < hi; ++k) ce += s_ce[k];
-        }
-        fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, 0.0, 0xffu, aD, aO, aC);
-#else
-#pragma unroll 1
-        for (int k = lo; k < hi; ++k) {
-          const double ce = s_ce[k];
-          double el = 0.0;
-          unsigned m = 0xffu;
-#if FVM_EDGE_USES_EL
-          el = s_el[k];
-#endif
-#if FVM_EDGE_MASKED
-          m = s_mask[k];
-#endif
-          double D = 0.0, O = 0.0, C = 0.0;
-          fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, el, m, D, O, C);
-          aD += D;
-          aO += O;
-          aC += C;
-        }
-#endif
-        sD += aD;
-        sC += aC;
-#if FVM_MODE != FVM_MODE_RESIDUAL
-        // Dirichlet rows keep their pattern but store explicit zeros off the diagonal
-        if (dir) aO = 0.0;
-#if FVM_STAGE_OUT
-        out[s] = aO;
-#else
-        a.data[d.s0 + s] = aO;
-#endif
-#endif
-      }
-#if FVM_GROUP > 1
-      // join the lanes of the group: fixed xor tree (deterministic)
-#pragma unroll
-      for (int w = FVM_GROUP / 2; w > 0; w >>= 1) {
-        sD += __shfl_xor_sync(0xffffffffu, sD, w);
-        sC += __shfl_xor_sync(0xffffffffu, sC, w);
-        ds = max(ds, __shfl_xor_sync(0xffffffffu, ds, w));
-      }
-#endif
-      if (live && gl == 0) {
-        double x2 = x02, cvv = 0.0;
 #if FVM_STAGE_CV
         cvv = s_cv[g];
 #endif
@@ -447,7 +476,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
           vm = s_vm[g];
 #endif
           double VL = 0.0, VC = 0.0;
-          fvm_vertex(u0, cvv, x00, x01, x2, vm, VL, VC);
+          fvm_vertex(u0, cvv, x00, x01, x02, vm, VL, VC);
           sD += VL;
           sC += VC;
         }
@@ -458,41 +487,30 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
         double out_vec = sC;
 #endif
 #if FVM_HAS_DIRICHLET
+        const int dir = s_dir[g];
         if (dir) {
           double dc = 0.0, dv = 0.0;
-          fvm_dirichlet(dir, u0, x00, x01, x2, dc, dv);
+          fvm_dirichlet(dir, u0, x00, x01, x02, dc, dv);
           sD = dc;       // row := coeff * e_row
           out_vec = dv;  // rhs := -affine (linear) / F := condition(u) (residual)
+#if FVM_MODE != FVM_MODE_RESIDUAL
+          // Dirichlet rows keep their pattern but store explicit zeros off the
+          // diagonal (ordered after pass A's stores by the __syncwarp above)
+#pragma unroll 1
+          for (int s = b; s < e; ++s) a.data[d_s0 + s] = 0.0;
+#endif
         }
 #endif
 #if FVM_MODE != FVM_MODE_RESIDUAL
-#if FVM_STAGE_OUT
-        out[ds] = sD;
-#else
-        a.data[d.s0 + ds] = sD;
-#endif
+        a.data[d_s0 + b + (int)s_dg[g]] = sD;
 #endif
 #if FVM_MODE != FVM_MODE_JACOBIAN
-        a.vec[d.r0 + g] = out_vec;
+        a.vec[d_r0 + g] = out_vec;
 #endif
       }
-#if FVM_STAGE_OUT
-      {
-        // coalesced copy-out of the CSR values of this warp's rows: they are
-        // consecutive, so are their slots; no other warp touches this range
-        constexpr int RPW = 32 / FVM_GROUP;  // rows per warp and chunk
-        const int gw = g0 + (ct >> 5) * RPW;
-        if (gw < d.nr) {
-          const int ge = min(gw + RPW, d.nr);
-          const int sbeg = s_rp[gw] - d.s0, send = s_rp[ge] - d.s0;
-          __syncwarp();
-          for (int s = sbeg + (ct & 31); s < send; s += 32) a.data[d.s0 + s] = out[s];
-        }
-      }
-#endif
     }
     // ---- release the stage to the producer (all lanes of this warp are done)
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) fvm_mbar_arrive(empty + st);
+    if (lane == 0) fvm_mbar_arrive(empty + st);
   }
 }

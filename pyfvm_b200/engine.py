@@ -52,7 +52,6 @@ class KernelOpts(ctypes.Structure):
         ("consumer_warps", c_int32),
         ("stages", c_int32),
         ("ctas_per_sm", c_int32),
-        ("group", c_int32),
     ]
 
 
@@ -237,7 +236,6 @@ class Engine:
                 consumer_warps=functors.consumer_warps,
                 stages=functors.stages,
                 ctas_per_sm=functors.ctas_per_sm,
-                group=functors.group,
             )
             self._ck(
                 self.lib.fvm_kernel_create(
@@ -355,7 +353,8 @@ class DeviceMesh:
     TILE_DTYPE = numpy.dtype(
         [("h0", "<i8"), ("r0", "<i4"), ("nr", "<i4"), ("s0", "<i4"), ("nsl", "<i4"),
          ("nhe", "<i4"), ("own_start", "<i4"), ("own_count", "<i4"), ("lo_start", "<i4"),
-         ("lo_count", "<i4"), ("hi_start", "<i4"), ("hi_count", "<i4"), ("pad", "<i4", (3,))]
+         ("lo_count", "<i4"), ("hi_start", "<i4"), ("hi_count", "<i4"), ("pad", "<i4", (3,)),
+         ("wb", "<u2", (16,))]
     )
 
     def stats(self):

@@ -27,7 +27,6 @@ def main():
     ap.add_argument("--stages", default="2")
     ap.add_argument("--ctas", default="0")
     ap.add_argument("--factor", default="1")
-    ap.add_argument("--group", default="")
     ap.add_argument("--fmad", type=int, default=0)
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--steps", type=int, default=50)
@@ -57,13 +56,12 @@ def main():
         print(dm.stats(), flush=True)
         data = eng.alloc(8 * dm.nnz)
         vec = eng.alloc(8 * n)
-        groups = ints(args.group) if args.group else [8 if args.cube else 1]
-        for w, st, ct, fc, gr in itertools.product(
-            ints(args.warps), ints(args.stages), ints(args.ctas), ints(args.factor), groups
+        for w, st, ct, fc in itertools.product(
+            ints(args.warps), ints(args.stages), ints(args.ctas), ints(args.factor)
         ):
             fun = codegen.generate(
                 lowered, args.mode, [None] * len(lowered.edge), [None] * len(lowered.vertex),
-                tune={"consumer_warps": w, "stages": st, "ctas_per_sm": ct, "factor_ce": fc, "group": gr},
+                tune={"consumer_warps": w, "stages": st, "ctas_per_sm": ct, "factor_ce": fc},
             )
             try:
                 k = eng.kernel(fun, fmad=bool(args.fmad))
@@ -74,13 +72,13 @@ def main():
                     dm.launch(k, dirid=d_dir.ptr, u=u.ptr, data=data.ptr, vec=vec.ptr)
                 ms = eng.timer_end() / args.steps
             except engine.FvmError as e:
-                print(f"q={q} warps={w} stages={st} ctas={ct} factor={fc} group={gr}: FAILED {str(e)[:100]}")
+                print(f"q={q} warps={w} stages={st} ctas={ct} factor={fc}: FAILED {str(e)[:100]}")
                 continue
             alg = bench.algorithmic_bytes(
                 dm.R, dm.nnz, n, dim, fun.uses_x, fun.uses_el, "assembly" if args.mode != 1 else "residual"
             )
             print(
-                f"q={q} warps={w} stages={st} ctas={ct} factor={fc} group={gr} fmad={args.fmad}: {ms:.4f} ms  "
+                f"q={q} warps={w} stages={st} ctas={ct} factor={fc} fmad={args.fmad}: {ms:.4f} ms  "
                 f"{alg / ms / 1e6:.0f} GB/s alg  {dm.R / ms / 1e6:.1f} Gcontrib/s  "
                 f"{k.info(dm)} tiles={dm.n_tiles}",
                 flush=True,
