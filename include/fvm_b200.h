@@ -111,7 +111,7 @@ int fvm_mesh_info(fvm_mesh* mesh, int64_t* nnz, int64_t* n_halfedges, int32_t* n
  * gathered from global memory instead), tile quantum, tiles, half-edges */
 int fvm_mesh_stats(fvm_mesh* mesh, int64_t* out, int n);
 /* copy an internal layout array to the host for inspection / tests:
- * 0 = tile descriptors (96 B each), 1 = packed slot metadata (4 B per slot),
+ * 0 = tile descriptors (128 B each), 1 = packed slot metadata (4 B per slot),
  * 2 = ce_ratios in half-edge order (8 B per half-edge) */
 int fvm_mesh_debug_copy(fvm_mesh* mesh, int which, void* out, size_t bytes);
 /* CSR pattern to host: indptr[n_rows+1], indices[nnz] (local vertex ids) */
@@ -130,7 +130,7 @@ typedef struct fvm_kernel_opts {
   int32_t mode;           /* FVM_LINEAR / FVM_RESIDUAL / FVM_JACOBIAN               */
   uint32_t flags;         /* FVM_KF_* bits; must equal the prelude's FVM_FLAGS      */
   int32_t fmad;           /* 0: --fmad=false (numpy-like rounding), 1: allow FMA    */
-  int32_t consumer_warps; /* math warps per CTA (1,2,4,8,16); = FVM_CONSUMER_WARPS      */
+  int32_t consumer_warps; /* math warps per CTA (1..16); = FVM_CONSUMER_WARPS           */
   int32_t stages;         /* shared-memory ring depth; must equal FVM_STAGES        */
   int32_t ctas_per_sm;    /* persistent CTAs per SM, 0 = as many as fit             */
 } fvm_kernel_opts;

@@ -10,10 +10,11 @@
 //   vertices   [row_base+r0, +nr) -> cv / dir_id / vmask slices
 // Per-vertex data that slots GATHER (coordinates, u) is staged as a tile-local
 // table: the tile's own vertices (plus a margin of a few vertices either side),
-// then up to two "halo" ranges holding the columns below / above the tile
-// (lo / hi).  slot_meta carries each slot's index into that table, so
-// the math warps never issue a global load.  Ranges start at even vertices and
-// have even length: every bulk copy is 16-byte aligned for 8-byte elements.
+// then up to FVM_NHALO "halo" ranges holding the columns outside the tile (a
+// structured triangle mesh needs 2, a structured tetrahedral mesh 8).  slot_meta
+// carries each slot's index into that table, so the math warps never issue a
+// global load.  Ranges start at even vertices and have even length: every bulk
+// copy is 16-byte aligned for 8-byte elements.
 //
 // slot_meta packs, per CSR slot, everything the slot-parallel pass needs:
 //   bits  0..11  first half-edge of the slot, relative to the tile   (< 4096)
@@ -21,20 +22,17 @@
 //   bits 20..31  index of the slot's column in the tile's vertex table
 //                (FVM_XLOC_NONE: not covered -> cold global gather)
 // The pattern build sizes the tiles so that these ranges always hold.
-#define FVM_WSPLIT 16  // a tile's rows are pre-split into this many equal-work ranges
-struct FvmTileDesc {   // 96 bytes, one per tile
+#define FVM_NHALO 8
+struct FvmTileDesc {  // 128 bytes, one per tile
   long long h0;
   int r0, nr;
   int s0, nsl;
   int nhe;
-  int own_start, own_count;  // vertices [own_start, +own_count) = rows of the tile (+ alignment)
-  int lo_start, lo_count;    // halo below the tile (count 0: not covered)
-  int hi_start, hi_count;    // halo above the tile
-  int pad[3];
-  // wb[i] = first row (tile-local) of work range i, i in 1..15 (wb[0] = 0, range 16
-  // ends at nr): ranges hold about the same number of half-edges + slots.  A math
-  // warp owns FVM_WSPLIT / FVM_CONSUMER_WARPS consecutive ranges.
-  unsigned short wb[FVM_WSPLIT];
+  int own_start, own_count;  // vertices [own_start, +own_count) = rows of the tile (+ margin)
+  int nhalo;                 // halo ranges in use
+  int hstart[FVM_NHALO];     // first vertex of every halo range (ascending, disjoint)
+  unsigned short hcount[FVM_NHALO];
+  int pad[10];
 };
 
 #define FVM_META_LO_BITS 12
@@ -115,7 +113,7 @@ FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_r
   const unsigned he = (unsigned)max_he, sl = (unsigned)max_slots, nr = (unsigned)max_rows;
   unsigned o = 0;  // within a stage
   const unsigned xt = (unsigned)max_xtab;
-  L.desc = o;   o += 96;
+  L.desc = o;   o += 128;
   L.ce = o;     o += fvm_round16(he * 8u) + 16u;
   L.el = o;     o += (flags & FVM_F_EDGE_EL) ? fvm_round16(he * 8u) + 16u : 0u;
   L.mask = o;   o += (flags & FVM_F_EDGE_MASK) ? fvm_round16(he) + 16u : 0u;

@@ -25,24 +25,25 @@
 //                    per row, and the tile-local vertex table (own rows + the
 //                    halo ranges holding the neighbour columns) of coordinates
 //                    and u -- one or more tiles ahead of the math;
-//   consumer warps : each warp owns a run of consecutive rows of the tile (equal
-//                    work, pre-split by the pattern build) and sweeps it twice.
-//                    Pass A is SLOT-parallel: lane l takes CSR slot c+l of a
-//                    32-slot chunk, folds the slot's ce_ratios in half-edge order
-//                    out of shared memory (consecutive lanes read consecutive
-//                    addresses), evaluates the edge functor with x/u of its row and
-//                    column from the staged vertex table, stores the off-diagonal
-//                    value straight to the CSR array (consecutive lanes ->
-//                    consecutive slots: coalesced) and parks the slot's diagonal /
-//                    rhs share in shared memory.  The slot -> row map is rebuilt
-//                    per chunk from the staged row pointers with one REDUX + POPC.
-//                    Pass B is ROW-parallel: lane l folds the parked shares of row
-//                    r+l in slot order, adds the vertex term, applies the
-//                    Dirichlet row replacement in the same pass and stores the
-//                    diagonal value and the rhs / residual entry.
+//   consumer warps : sweep the tile twice.
+//                    Pass A is SLOT-parallel: the tile's CSR slots are cut into
+//                    32-slot chunks dealt round-robin to the warps; lane l takes
+//                    slot c+l, folds the slot's ce_ratios in half-edge order out of
+//                    shared memory (consecutive lanes read consecutive addresses),
+//                    evaluates the edge functor with x/u of its row and column
+//                    from the staged vertex table (slot_meta carries the row and
+//                    the table index), stores the off-diagonal value straight to
+//                    the CSR array (consecutive lanes -> consecutive slots:
+//                    coalesced) and parks the slot's diagonal / rhs share in
+//                    shared memory.  A named barrier over the math warps follows.
+//                    Pass B is ROW-parallel: the rows are dealt to the warps in
+//                    equal runs; lane l folds the parked shares of its row in slot
+//                    order, adds the vertex term, applies the Dirichlet row
+//                    replacement in the same pass and stores the diagonal value
+//                    and the rhs / residual entry.
 // Deterministic and atomic-free: a slot is the in-order sum of its half-edges, a
-// row the in-order sum of its slots -- never a function of tile boundaries, warp
-// ranges or the grid size, so a row-partitioned multi-GPU run is bit-identical
+// row the in-order sum of its slots -- never a function of tile boundaries, the
+// warp count or the grid size, so a row-partitioned multi-GPU run is bit-identical
 // to the single-GPU run.
 
 #ifndef M_PI
@@ -67,7 +68,6 @@
 
 static_assert(!(FVM_EDGE_USES_X || FVM_VERT_USES_X) || FVM_STAGE_X, "FVM_F_X missing");
 static_assert(!(FVM_EDGE_USES_U || FVM_VERT_USES_U) || FVM_STAGE_U, "FVM_F_U missing");
-static_assert(FVM_WSPLIT % FVM_CONSUMER_WARPS == 0, "FVM_CONSUMER_WARPS must divide FVM_WSPLIT");
 static_assert(FVM_MODE != FVM_MODE_RESIDUAL || !FVM_ACC_D, "residual mode has no D output");
 static_assert(FVM_MODE != FVM_MODE_JACOBIAN || !FVM_ACC_C, "Jacobian mode has no C output");
 static_assert(!(FVM_EDGE_FACTORED && (FVM_EDGE_USES_EL || FVM_EDGE_MASKED)),
@@ -148,8 +148,11 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
   const FvmStage g_meta = fvm_stage(a.slot_meta + d.s0, (unsigned)d.nsl * 4u);
   const FvmStage g_rp = fvm_stage(a.indptr + d.r0, (unsigned)(d.nr + 1) * 4u);
   total += g_ce.bytes + g_meta.bytes + g_rp.bytes;
-  // vertex table: own rows, halo below, halo above (even starts, even counts)
-  const unsigned n_tab = (unsigned)(d.own_count + d.lo_count + d.hi_count);
+  // vertex table: own rows, then the halo ranges (even starts, even counts)
+  unsigned n_tab = (unsigned)d.own_count;
+#pragma unroll
+  for (int i = 0; i < FVM_NHALO; ++i)
+    if (i < d.nhalo) n_tab += d.hcount[i];
 #if FVM_EDGE_USES_EL
   const FvmStage g_el = fvm_stage(a.he_el + d.h0, (unsigned)d.nhe * 8u);
   total += g_el.bytes;
@@ -200,11 +203,13 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
     if (d.own_count)
       fvm_bulk_g2s(dst, a.coords + (size_t)d.own_start * FVM_XS, (unsigned)d.own_count * vb, full);
     dst += (unsigned)d.own_count * vb;
-    if (d.lo_count)
-      fvm_bulk_g2s(dst, a.coords + (size_t)d.lo_start * FVM_XS, (unsigned)d.lo_count * vb, full);
-    dst += (unsigned)d.lo_count * vb;
-    if (d.hi_count)
-      fvm_bulk_g2s(dst, a.coords + (size_t)d.hi_start * FVM_XS, (unsigned)d.hi_count * vb, full);
+#pragma unroll
+    for (int i = 0; i < FVM_NHALO; ++i) {
+      if (i < d.nhalo) {
+        fvm_bulk_g2s(dst, a.coords + (size_t)d.hstart[i] * FVM_XS, (unsigned)d.hcount[i] * vb, full);
+        dst += (unsigned)d.hcount[i] * vb;
+      }
+    }
   }
 #endif
 #if FVM_STAGE_U
@@ -212,9 +217,13 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
     unsigned char* dst = stage + L.u;
     if (d.own_count) fvm_bulk_g2s(dst, a.u + d.own_start, (unsigned)d.own_count * 8u, full);
     dst += (unsigned)d.own_count * 8u;
-    if (d.lo_count) fvm_bulk_g2s(dst, a.u + d.lo_start, (unsigned)d.lo_count * 8u, full);
-    dst += (unsigned)d.lo_count * 8u;
-    if (d.hi_count) fvm_bulk_g2s(dst, a.u + d.hi_start, (unsigned)d.hi_count * 8u, full);
+#pragma unroll
+    for (int i = 0; i < FVM_NHALO; ++i) {
+      if (i < d.nhalo) {
+        fvm_bulk_g2s(dst, a.u + d.hstart[i], (unsigned)d.hcount[i] * 8u, full);
+        dst += (unsigned)d.hcount[i] * 8u;
+      }
+    }
   }
 #endif
 #if FVM_HAS_DIRICHLET
@@ -260,7 +269,7 @@ __device__ __forceinline__ FvmTileDesc fvm_load_desc(const FvmTileDesc* g) {
   ((int4*)&d)[2] = d2;
   ((int4*)&d)[3] = d3;
   ((int4*)&d)[4] = d4;
-  ((int4*)&d)[5] = d5;
+  ((int4*)&d)[5] = d5;  // .. hcount; the padding is not read
   return d;
 }
 
@@ -303,7 +312,6 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
   // ========================= consumer warps ==================================
   const int lane = threadIdx.x & 31;
   const int cw = (threadIdx.x >> 5) - 1;  // consumer warp id
-  constexpr int WR = FVM_WSPLIT / FVM_CONSUMER_WARPS;  // work ranges per warp
 
   int it = 0;
   for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
@@ -313,9 +321,9 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
     const FvmTileDesc* sd = (const FvmTileDesc*)(stage + L.desc);
     const int d_nr = sd->nr, d_s0 = sd->s0, d_nsl = sd->nsl, d_nhe = sd->nhe, d_r0 = sd->r0;
     const int v0 = a.row_base + d_r0;  // first vertex of the tile
-    // rows [ra, rb) of the tile belong to this warp
-    const int ra = cw == 0 ? 0 : (int)sd->wb[cw * WR];
-    const int rb = cw == FVM_CONSUMER_WARPS - 1 ? d_nr : (int)sd->wb[(cw + 1) * WR];
+    // pass B: rows [ra, rb) of the tile belong to this warp
+    const int ra = (d_nr * cw) / FVM_CONSUMER_WARPS;
+    const int rb = (d_nr * (cw + 1)) / FVM_CONSUMER_WARPS;
 
     const double* s_ce = (const double*)(stage + L.ce + fvm_shift(a.he_ce + sd->h0));
     const unsigned* s_meta = (const unsigned*)(stage + L.meta + fvm_shift(a.slot_meta + d_s0));
@@ -353,11 +361,11 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
         (const unsigned short*)(stage + L.dg + fvm_shift(a.row_diag + d_r0));
 #endif
 
-    if (ra < rb) {
+    {
       // ---------------- pass A: one lane per CSR slot -------------------------
-      const int sa = s_rp[ra] - d_s0, sb = s_rp[rb] - d_s0;  // this warp's slots
+      // 32-slot chunks dealt round-robin to the math warps
 #pragma unroll 1
-      for (int s = sa + lane; s < sb; s += 32) {
+      for (int s = cw * 32 + lane; s < d_nsl; s += FVM_NCT) {
         const unsigned meta = s_meta[s];
         const int lo = (int)(meta & FVM_META_LO_MASK);
         const int hi = (s + 1 < d_nsl) ? (int)(s_meta[s + 1] & FVM_META_LO_MASK) : d_nhe;
@@ -404,8 +412,13 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
 #if FVM_EDGE_FACTORED
           // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
           double ce = s_ce[lo];
+          if (hi - lo > 1) {  // the common interior case is two half-edges per slot
+            ce += s_ce[lo + 1];
+            if (hi - lo > 2) {
 #pragma unroll 1
-          for (int k = lo + 1; k < hi; ++k) ce += s_ce[k];
+              for (int k = lo + 2; k < hi; ++k) ce += s_ce[k];
+            }
+          }
           fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, 0.0, 0xffu, aD, aO, aC);
 #else
 #pragma unroll 1
@@ -437,7 +450,8 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
         s_accc[s] = aC;
 #endif
       }
-      __syncwarp();  // the parked shares are visible to the whole warp
+      // the parked shares (and pass A's CSR stores) are visible to all math warps
+      asm volatile("bar.sync 1, %0;" ::"n"(FVM_NCT) : "memory");
 
       // ---------------- pass B: one lane per matrix row ------------------------
       for (int g = ra + lane; g < rb; g += 32) {
@@ -495,7 +509,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
           out_vec = dv;  // rhs := -affine (linear) / F := condition(u) (residual)
 #if FVM_MODE != FVM_MODE_RESIDUAL
           // Dirichlet rows keep their pattern but store explicit zeros off the
-          // diagonal (ordered after pass A's stores by the __syncwarp above)
+          // diagonal (ordered after pass A's stores by the barrier above)
 #pragma unroll 1
           for (int s = b; s < e; ++s) a.data[d_s0 + s] = 0.0;
 #endif

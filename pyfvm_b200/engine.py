@@ -352,9 +352,8 @@ class DeviceMesh:
 
     TILE_DTYPE = numpy.dtype(
         [("h0", "<i8"), ("r0", "<i4"), ("nr", "<i4"), ("s0", "<i4"), ("nsl", "<i4"),
-         ("nhe", "<i4"), ("own_start", "<i4"), ("own_count", "<i4"), ("lo_start", "<i4"),
-         ("lo_count", "<i4"), ("hi_start", "<i4"), ("hi_count", "<i4"), ("pad", "<i4", (3,)),
-         ("wb", "<u2", (16,))]
+         ("nhe", "<i4"), ("own_start", "<i4"), ("own_count", "<i4"), ("nhalo", "<i4"),
+         ("hstart", "<i4", (8,)), ("hcount", "<u2", (8,)), ("pad", "<i4", (10,))]
     )
 
     def stats(self):
