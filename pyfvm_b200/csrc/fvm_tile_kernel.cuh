@@ -326,6 +326,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
     const int rb = (d_nr * (cw + 1)) / FVM_CONSUMER_WARPS;
 
     const double* s_ce = (const double*)(stage + L.ce + fvm_shift(a.he_ce + sd->h0));
+    const int ce_odd = (int)(fvm_shift(a.he_ce + sd->h0) >> 3);  // 1: s_ce[0] sits at 8 mod 16
     const unsigned* s_meta = (const unsigned*)(stage + L.meta + fvm_shift(a.slot_meta + d_s0));
     const int xoff = v0 - sd->own_start;  // table index of the tile's first row
     const int* s_rp = (const int*)(stage + L.rowptr + fvm_shift(a.indptr + d_r0));
@@ -411,14 +412,36 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
 #endif
 #if FVM_EDGE_FACTORED
           // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
+#if FVM_DIM == 3
+          // tetrahedra: ~10 half-edges per slot; read them two at a time, the first
+          // pair with one 16-byte load where it is 16-byte aligned
+          double ce;
+          int k = lo;
+          if (((lo ^ ce_odd) & 1) == 0 && hi - lo > 1) {
+            const double2 p = *(const double2*)(s_ce + lo);
+            ce = p.x + p.y;
+            k = lo + 2;
+          } else {
+            ce = s_ce[lo];
+            k = lo + 1;
+          }
+#pragma unroll 1
+          for (; k + 1 < hi; k += 2) {  // k keeps the parity of an aligned pair or of lo + 1
+            ce += s_ce[k];
+            ce += s_ce[k + 1];
+          }
+          if (k < hi) ce += s_ce[k];
+#else
+          // triangles: two half-edges per interior slot
           double ce = s_ce[lo];
-          if (hi - lo > 1) {  // the common interior case is two half-edges per slot
+          if (hi - lo > 1) {
             ce += s_ce[lo + 1];
             if (hi - lo > 2) {
 #pragma unroll 1
               for (int k = lo + 2; k < hi; ++k) ce += s_ce[k];
             }
           }
+#endif
           fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, 0.0, 0xffu, aD, aO, aC);
 #else
 #pragma unroll 1
