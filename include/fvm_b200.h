@@ -58,6 +58,11 @@ const char* fvm_last_error(void);
 int fvm_ctx_create(int device, fvm_ctx** out);
 int fvm_ctx_destroy(fvm_ctx* ctx);
 int fvm_ctx_sync(fvm_ctx* ctx);
+/* run every later call of this ctx on a caller-owned CUDA stream (cudaStream_t passed
+ * as void*, e.g. torch.cuda.current_stream().cuda_stream) so that the library's
+ * kernels are stream-ordered with the caller's NCCL collectives; use_external = 0
+ * returns to the ctx's own stream.  Synchronises the old stream first. */
+int fvm_ctx_set_stream(fvm_ctx* ctx, void* cuda_stream, int use_external);
 /* name, SM count, bytes of global memory of the ctx's device */
 int fvm_ctx_info(fvm_ctx* ctx, char* name, size_t name_len, int* sm_count, size_t* mem_bytes);
 
@@ -162,6 +167,26 @@ int fvm_norm2(fvm_ctx* ctx, const double* x_dev, int64_t n, double* out);
 /* dst[i] = src[idx[i]]: halo pack for the row-partitioned multi-GPU path */
 int fvm_gather_f64(fvm_ctx* ctx, const double* src_dev, const int32_t* idx_dev, int64_t n,
                    double* dst_dev);
+/* ---- halo exchange over peer memory (one 8-GPU NVLink/NVSwitch box) ----------
+ * The row-partitioned residual / Jacobian need u at ghost vertices.  Each rank
+ * exports its local u arrays and a flag word per peer with CUDA IPC; a peer maps
+ * them once (fvm_ipc_open) and then, every evaluation, PUSHES the owned values its
+ * neighbour needs straight into that neighbour's ghost slots (P2P stores over
+ * NVLink) and releases the epoch into the neighbour's flag; the neighbour's
+ * fvm_halo_wait (a stream-ordered spin kernel with a timeout) acquires it before
+ * the tile kernel runs.  No host round trip, no staging buffer, no NCCL call. */
+int fvm_ipc_export(fvm_ctx* ctx, void* ptr_dev, unsigned char* handle64);
+int fvm_ipc_open(fvm_ctx* ctx, const unsigned char* handle64, void** out_dev);
+int fvm_ipc_close(fvm_ctx* ctx, void* ptr_dev);
+/* peer_dst_dev[i] = src_dev[send_index_dev[i]], i < n; then (stream-ordered,
+ * system-scope release) *peer_flag_dev = epoch.  peer_flag_dev may be NULL. */
+int fvm_halo_push(fvm_ctx* ctx, const double* src_dev, const int32_t* send_index_dev, int64_t n,
+                  double* peer_dst_dev, uint64_t* peer_flag_dev, uint64_t epoch);
+/* stream-ordered wait until every flags_dev[i] (device array of n_flags device
+ * pointers) has reached epoch; after timeout_s seconds sets *timed_out_dev = 1 and
+ * returns instead of hanging. */
+int fvm_halo_wait(fvm_ctx* ctx, const uint64_t* const* flags_dev, int n_flags, uint64_t epoch,
+                  double timeout_s, int32_t* timed_out_dev);
 /* y += a*x (Newton update on the device) */
 int fvm_axpy(fvm_ctx* ctx, double a, const double* x_dev, double* y_dev, int64_t n);
 

@@ -1,0 +1,372 @@
+"""Row-partitioned multi-GPU path: one process per GPU, vertices
+split into contiguous ranges, every rank assembles complete owned rows.
+
+* ``Partition(mesh, rank, world)`` cuts a global mesh: the records (columns of
+  ``idx_hierarchy``) with at least one owned endpoint, the local vertex set
+  ``ghost-low | owned | ghost-high`` (monotone in the global numbering, so the
+  fold order of every owned row equals the single-GPU run: results are
+  bit-identical), and the halo plan.  ``Partition.mesh`` exposes the meshplex
+  attribute contract for the local piece, with the GLOBAL
+  control volumes and boundary flags.
+* Linear assembly needs no communication at all.
+* Residual / Jacobian need ``u`` at the ghost vertices, once per evaluation:
+  - ``TorchHalo``: grouped ``isend``/``irecv`` through ``torch.distributed``
+    (NCCL on GPUs, gloo in the CPU tests); ghosts of one owner are contiguous in
+    the local numbering, so the receive side needs no unpack;
+  - ``PeerHalo``: CUDA-IPC peer memory.  Every rank PUSHES the owned values a
+    neighbour needs straight into that neighbour's ghost slots (P2P stores over
+    NVLink) and releases an epoch flag; the neighbour's stream waits on the flag
+    (``fvm_halo_push`` / ``fvm_halo_wait``).  ``u`` is double-buffered by epoch
+    parity so a fast rank never overwrites values a slow one still reads.
+
+The reference is single-process; there is no reference code for this file.
+"""
+import ctypes
+from ctypes import byref, c_void_p
+
+import numpy
+
+from . import codegen
+from .engine import Engine
+
+
+def row_bounds(n, world):
+    """Contiguous, balanced vertex ranges: rank r owns [b[r], b[r+1])."""
+    return [(n * r) // world for r in range(world + 1)]
+
+
+class LocalMesh:
+    """The meshplex attribute contract for one rank's piece of a mesh.  Records
+    are kept as a flat list: ``idx_hierarchy`` has shape (2, R_local) and "cell
+    masks" are per record."""
+
+    def __init__(self, points, idx, ce, ei_dot_ei, cv, boundary, rec_global, cell_of_record,
+                 parent):
+        self.points = points
+        nc = numpy.zeros((len(points), 3))
+        nc[:, : points.shape[1]] = points
+        self.node_coords = nc
+        self.idx_hierarchy = idx
+        self.ce_ratios = ce
+        self.ei_dot_ei = ei_dot_ei
+        self.control_volumes = cv
+        self.is_boundary_point = boundary
+        self._rec_global = rec_global
+        self._cell_of_record = cell_of_record
+        self._parent = parent
+
+    def get_vertex_mask(self, subdomain=None):
+        if subdomain is None:
+            return numpy.s_[:]
+        mask = numpy.asarray(subdomain.is_inside(self.node_coords.T), dtype=bool)
+        if getattr(subdomain, "is_boundary_only", False):
+            mask = mask & self.is_boundary_point
+        return mask
+
+    def get_cell_mask(self, subdomain=None):
+        """Per local record: is the record's cell inside ``subdomain``?"""
+        if subdomain is None:
+            return numpy.s_[:]
+        cells = numpy.asarray(self._parent.get_cell_mask(subdomain))
+        return cells[self._cell_of_record]
+
+
+class Partition:
+    """Rank ``rank``'s share of ``mesh`` (a global mesh every rank can see)."""
+
+    def __init__(self, mesh, rank, world, bounds=None):
+        idx = numpy.asarray(mesh.idx_hierarchy)
+        ncell = idx.shape[-1]
+        i0 = idx[0].reshape(-1)
+        i1 = idx[1].reshape(-1)
+        pts = numpy.asarray(mesh.points if hasattr(mesh, "points") else mesh.node_coords)
+        n = len(pts)
+        self.rank, self.world, self.n_global = rank, world, n
+        self.bounds = list(bounds) if bounds is not None else row_bounds(n, world)
+        lo, hi = self.bounds[rank], self.bounds[rank + 1]
+        own0 = (i0 >= lo) & (i0 < hi)
+        own1 = (i1 >= lo) & (i1 < hi)
+        rec = numpy.nonzero(own0 | own1)[0]  # ascending: the global record order is kept
+        verts = numpy.unique(numpy.concatenate([i0[rec], i1[rec], numpy.arange(lo, hi)]))
+        self.verts = verts  # local -> global vertex id, ascending
+        self.n_local = len(verts)
+        self.n_ghost_lo = int(numpy.searchsorted(verts, lo))
+        self.n_owned = hi - lo
+        self.row_range = (self.n_ghost_lo, self.n_owned)
+        l0 = numpy.searchsorted(verts, i0[rec])
+        l1 = numpy.searchsorted(verts, i1[rec])
+        # flat record id -> cell id (the last axis of idx_hierarchy is the cell)
+        cell_of_record = rec % ncell
+        self.mesh = LocalMesh(
+            points=numpy.ascontiguousarray(pts[verts]),
+            idx=numpy.stack([l0, l1]).astype(numpy.int64),
+            ce=numpy.asarray(mesh.ce_ratios).reshape(-1)[rec],
+            ei_dot_ei=numpy.asarray(mesh.ei_dot_ei).reshape(-1)[rec],
+            cv=numpy.asarray(mesh.control_volumes)[verts],
+            boundary=numpy.asarray(mesh.is_boundary_point)[verts],
+            rec_global=rec,
+            cell_of_record=cell_of_record,
+            parent=mesh,
+        )
+        # ---- halo plan -------------------------------------------------------
+        # receive: ghosts sorted by global id are grouped by owner (owners are
+        # contiguous ranges), so each owner's ghosts form one local slice
+        ghost = numpy.concatenate([verts[: self.n_ghost_lo], verts[self.n_ghost_lo + self.n_owned:]])
+        ghost_local = numpy.concatenate(
+            [numpy.arange(self.n_ghost_lo), numpy.arange(self.n_ghost_lo + self.n_owned, self.n_local)]
+        )
+        owner = numpy.searchsorted(self.bounds, ghost, side="right") - 1
+        self.recv = {}  # peer -> (first local ghost slot, count)
+        for p in numpy.unique(owner):
+            sel = ghost_local[owner == p]
+            assert sel[-1] - sel[0] + 1 == len(sel)
+            self.recv[int(p)] = (int(sel[0]), len(sel))
+        # send: my vertices that appear in a record whose other endpoint peer p owns
+        # (= exactly p's ghosts owned by me), ascending -> same order on both sides
+        self.send = {}  # peer -> local indices (int32) of the owned values p needs
+        a = numpy.concatenate([i0[rec][own0[rec] & ~own1[rec]], i1[rec][own1[rec] & ~own0[rec]]])
+        b = numpy.concatenate([i1[rec][own0[rec] & ~own1[rec]], i0[rec][own1[rec] & ~own0[rec]]])
+        if len(a):
+            bowner = numpy.searchsorted(self.bounds, b, side="right") - 1
+            for p in numpy.unique(bowner):
+                mine = numpy.unique(a[bowner == p])
+                self.send[int(p)] = numpy.searchsorted(verts, mine).astype(numpy.int32)
+        self.neighbours = sorted(set(self.recv) | set(self.send))
+
+    def owned(self, x_global):
+        lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        return numpy.ascontiguousarray(x_global[lo:hi])
+
+
+# ---------------------------------------------------------------------------
+# halo exchange back ends
+# ---------------------------------------------------------------------------
+class TorchHalo:
+    """``u_local`` is a torch tensor (CPU with gloo, CUDA with NCCL); one grouped
+    isend/irecv round per evaluation."""
+
+    def __init__(self, part, group=None):
+        import torch
+
+        self.part, self.group = part, group
+        self._idx = {p: torch.from_numpy(ix.astype(numpy.int64)) for p, ix in part.send.items()}
+
+    def exchange(self, u_local):
+        import torch
+        import torch.distributed as dist
+
+        ops, keep = [], []
+        for p, ix in sorted(self._idx.items()):
+            if ix.device != u_local.device:
+                ix = self._idx[p] = ix.to(u_local.device)
+            buf = u_local.index_select(0, ix)  # pack
+            keep.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, p, group=self.group))
+        for p, (start, count) in sorted(self.part.recv.items()):
+            ops.append(dist.P2POp(dist.irecv, u_local[start : start + count], p, group=self.group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        return u_local
+
+
+class PeerHalo:
+    """CUDA-IPC peer memory: push into the neighbour's ghost slots + epoch flag.
+
+    One device allocation per rank, exported once:
+    ``[u buffer 0 | u buffer 1 | flags (one uint64 per rank) | timeout flag]``.
+    """
+
+    TIMEOUT_S = 20.0
+
+    def __init__(self, part, eng, group=None):
+        import torch.distributed as dist
+
+        self.part, self.eng = part, eng
+        lib = eng.lib
+        nl = part.n_local
+        self.ustride = (8 * nl + 255) & ~255
+        self.flag_off = 2 * self.ustride
+        nbytes = self.flag_off + 8 * part.world + 64
+        self.buf = eng.alloc(nbytes)
+        eng._ck(lib.fvm_dev_memset(eng.ctx, self.buf.ptr, 0, nbytes))
+        eng.sync()
+        handle = ctypes.create_string_buffer(64)
+        eng._ck(lib.fvm_ipc_export(eng.ctx, self.buf.ptr, handle))
+        mine = {
+            "handle": handle.raw,
+            "ustride": self.ustride,
+            "flag_off": self.flag_off,
+            "recv": part.recv,  # owner -> (first ghost slot, count) in MY local numbering
+        }
+        infos = [None] * part.world
+        dist.all_gather_object(infos, mine, group=group)
+        self.peer = {}
+        for p in part.neighbours:
+            base = c_void_p()
+            eng._ck(lib.fvm_ipc_open(eng.ctx, infos[p]["handle"], byref(base)))
+            start, count = infos[p]["recv"][part.rank]
+            assert count == len(part.send[p]), "halo plans of the two sides disagree"
+            self.peer[p] = {
+                "base": base.value,
+                "ustride": infos[p]["ustride"],
+                "ghost_byte_off": 8 * start,
+                "flag": base.value + infos[p]["flag_off"] + 8 * part.rank,
+                "send": eng.to_device(part.send[p]),
+                "n": count,
+            }
+        # device array of pointers to the flags my neighbours write
+        flags = numpy.array(
+            [self.buf.ptr + self.flag_off + 8 * p for p in sorted(part.recv)], dtype=numpy.uint64
+        )
+        self.flag_ptrs = eng.to_device(flags) if len(flags) else None
+        self.n_flags = len(flags)
+        self.timeout_ptr = self.buf.ptr + self.flag_off + 8 * part.world
+        self.epoch = 0
+        dist.barrier(group=group)  # every mapping exists before the first push
+
+    def u_ptr(self, k):
+        return self.buf.ptr + k * self.ustride
+
+    def next_buffer(self):
+        """Buffer index the next exchange will use (owned part to be filled first)."""
+        return (self.epoch + 1) & 1
+
+    def exchange(self):
+        """Push my owned boundary values of buffer ``next_buffer()`` to the
+        neighbours, wait for theirs; returns the device address of the complete
+        local ``u``.  Everything is stream-ordered on the ctx stream."""
+        eng, lib = self.eng, self.eng.lib
+        self.epoch += 1
+        k = self.epoch & 1
+        src = self.u_ptr(k)
+        for p, d in sorted(self.peer.items()):
+            dst = d["base"] + k * d["ustride"] + d["ghost_byte_off"]
+            eng._ck(lib.fvm_halo_push(eng.ctx, src, d["send"].ptr, d["n"], dst, d["flag"], self.epoch))
+        if self.n_flags:
+            eng._ck(
+                lib.fvm_halo_wait(
+                    eng.ctx, self.flag_ptrs.ptr, self.n_flags, self.epoch, self.TIMEOUT_S,
+                    self.timeout_ptr,
+                )
+            )
+        return src
+
+    def check_timeout(self):
+        flag = numpy.zeros(1, dtype=numpy.int32)
+        self.eng._ck(self.eng.lib.fvm_d2h(self.eng.ctx, flag.ctypes.data, self.timeout_ptr, 4))
+        if flag[0]:
+            raise RuntimeError("halo exchange timed out waiting for a neighbour rank")
+
+    def close(self):
+        self.eng.sync()
+        for d in self.peer.values():
+            self.eng.lib.fvm_ipc_close(self.eng.ctx, d["base"])
+        self.peer = {}
+
+
+# ---------------------------------------------------------------------------
+# distributed problems
+# ---------------------------------------------------------------------------
+def discretize_linear(obj, part, device=None, fmad=False):
+    """Owned rows of ``pyfvm.discretize_linear`` on this rank: a CSR block of shape
+    (n_owned, n_global) with GLOBAL column ids, and the owned rhs.  No collective."""
+    from scipy import sparse
+
+    from .problem import LinearProblem
+
+    lp = LinearProblem(obj, part.mesh, device=device, fmad=fmad, row_range=part.row_range)
+    A_local, rhs = lp.assemble()
+    A = sparse.csr_matrix(
+        (A_local.data, part.verts[A_local.indices].astype(numpy.int32), A_local.indptr),
+        shape=(part.n_owned, part.n_global),
+    )
+    return A, rhs
+
+
+class DistributedFvm:
+    """``pyfvm.discretize`` on one rank of a row partition: ``eval(u_owned)`` and
+    ``jacobian_values(u_owned)`` exchange the ghost values first."""
+
+    def __init__(self, obj, part, halo="peer", device=None, fmad=False, group=None):
+        from .problem import _DeviceProblem
+
+        self.part = part
+        self.s = _DeviceProblem(
+            obj, part.mesh, "nonlinear", device=device, fmad=fmad, row_range=part.row_range
+        )
+        self.eng = self.s.eng
+        self.kind = halo
+        if halo == "peer":
+            self.halo = PeerHalo(part, self.eng, group=group)
+        elif halo == "torch":
+            import torch
+
+            self.halo = TorchHalo(part, group=group)
+            self.u_t = torch.zeros(part.n_local, dtype=torch.float64, device=f"cuda:{self.eng.device}")
+        else:
+            raise ValueError("halo must be 'peer' or 'torch'")
+        self.F = self.eng.alloc(8 * max(1, part.n_owned))
+
+    # -- device-resident steps ------------------------------------------------
+    def set_owned(self, u_owned):
+        """Host -> device: the owned part of the next ``u``."""
+        u_owned = numpy.ascontiguousarray(u_owned, dtype=numpy.float64)
+        assert u_owned.shape == (self.part.n_owned,)
+        off = 8 * self.part.n_ghost_lo
+        if self.kind == "peer":
+            dst = self.halo.u_ptr(self.halo.next_buffer()) + off
+            self.eng._ck(self.eng.lib.fvm_h2d(self.eng.ctx, dst, u_owned.ctypes.data, u_owned.nbytes))
+        else:
+            import torch
+
+            self.u_t[self.part.n_ghost_lo : self.part.n_ghost_lo + self.part.n_owned] = (
+                torch.from_numpy(u_owned).to(self.u_t.device)
+            )
+
+    def exchange(self):
+        """Ghost values in place; returns the device address of the local ``u``."""
+        if self.kind == "peer":
+            return self.halo.exchange()
+        import torch
+
+        self.halo.exchange(self.u_t)
+        torch.cuda.current_stream().synchronize()  # NCCL stream -> ctx stream hand-off
+        return self.u_t.data_ptr()
+
+    def residual_device(self, u_ptr):
+        self.s.launch(codegen.MODE_RESIDUAL, u_ptr=u_ptr, vec_ptr=self.F.ptr)
+
+    def jacobian_device(self, u_ptr):
+        self.s.launch(codegen.MODE_JACOBIAN, u_ptr=u_ptr, data_ptr=self.s.data.ptr)
+
+    # -- host API ---------------------------------------------------------------
+    def eval(self, u_owned):
+        """Owned rows of ``f.eval(u)`` [README:121]."""
+        self.set_owned(u_owned)
+        self.residual_device(self.exchange())
+        out = numpy.empty(self.part.n_owned)
+        self.F.download(out)
+        if self.kind == "peer":
+            self.halo.check_timeout()
+        return out
+
+    def jacobian_values(self, u_owned):
+        """Owned rows of ``jacobian.get_linear_operator(u)`` [README:116] as a CSR
+        block (n_owned, n_global) with global column ids."""
+        from scipy import sparse
+
+        self.set_owned(u_owned)
+        self.jacobian_device(self.exchange())
+        data = numpy.empty(self.s.nnz)
+        self.s.data.download(data)
+        indptr, indices = self.s.dmesh.pattern()
+        return sparse.csr_matrix(
+            (data, self.part.verts[indices].astype(numpy.int32), indptr),
+            shape=(self.part.n_owned, self.part.n_global),
+        )
+
+    def norm2_owned_sq(self):
+        """Sum of squares of the owned residual (deterministic); the caller adds
+        the ranks' values with one all-reduce of a double."""
+        return self.eng.norm2(self.F.ptr, self.part.n_owned) ** 2

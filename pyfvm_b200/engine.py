@@ -62,6 +62,7 @@ SYMBOLS = {
     "fvm_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
     "fvm_ctx_destroy": (c_int, [c_void_p]),
     "fvm_ctx_sync": (c_int, [c_void_p]),
+    "fvm_ctx_set_stream": (c_int, [c_void_p, c_void_p, c_int]),
     "fvm_ctx_info": (c_int, [c_void_p, c_char_p, c_size_t, POINTER(c_int), POINTER(c_size_t)]),
     "fvm_dev_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "fvm_dev_free": (c_int, [c_void_p, c_void_p]),
@@ -97,6 +98,17 @@ SYMBOLS = {
     ),
     "fvm_norm2": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double)]),
     "fvm_gather_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "fvm_ipc_export": (c_int, [c_void_p, c_void_p, c_char_p]),
+    "fvm_ipc_open": (c_int, [c_void_p, c_char_p, POINTER(c_void_p)]),
+    "fvm_ipc_close": (c_int, [c_void_p, c_void_p]),
+    "fvm_halo_push": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, ctypes.c_uint64],
+    ),
+    "fvm_halo_wait": (
+        c_int,
+        [c_void_p, c_void_p, c_int, ctypes.c_uint64, c_double, c_void_p],
+    ),
     "fvm_axpy": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_int64]),
 }
 

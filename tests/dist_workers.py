@@ -1,0 +1,149 @@
+"""Worker bodies of the multi-process tests (importable by ``spawn``)."""
+import os
+import sys
+
+import numpy
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _mesh(kind, n):
+    from pyfvm_b200 import meshes
+    from tests import problems
+
+    p, c = (problems.rectangle(n, n - 3) if kind == "rect" else problems.cube(n))
+    p, c = meshes.jitter(p, c, scale=0.2, seed=0)
+    return meshes.Mesh(p, c)
+
+
+def gloo_halo_worker(rank, world, port, kind, n, out_dir):
+    """CPU / gloo: partition, halo exchange of u, and the oracle run per rank on
+    the local piece; writes what the parent compares against the global oracle."""
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    from pyfvm_b200 import dist as fd
+    from tests import problems
+
+    dist.init_process_group(
+        "gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world
+    )
+    try:
+        mesh = _mesh(kind, n)
+        nglob = len(mesh.points)
+        part = fd.Partition(mesh, rank, world)
+        u_glob = numpy.random.default_rng(7).standard_normal(nglob)
+        # owned values only; ghosts arrive through the exchange
+        u_loc = torch.full((part.n_local,), float("nan"), dtype=torch.float64)
+        g0 = part.n_ghost_lo
+        u_loc[g0 : g0 + part.n_owned] = torch.from_numpy(part.owned(u_glob))
+        fd.TorchHalo(part).exchange(u_loc)
+        u_loc = u_loc.numpy()
+        assert numpy.array_equal(u_loc, u_glob[part.verts]), "halo exchange delivered wrong values"
+
+        # the oracle on the local piece: owned rows must equal the global rows
+        f, jac = oracle.discretize(problems.bratu(oracle.form_language), part.mesh)
+        F = f.eval(u_loc)[g0 : g0 + part.n_owned]
+        J = jac.get_linear_operator(u_loc)[g0 : g0 + part.n_owned]
+        A, b = oracle.discretize_linear(problems.convection_diffusion(oracle.form_language), part.mesh)
+        A = A[g0 : g0 + part.n_owned]
+        numpy.savez(
+            os.path.join(out_dir, f"rank{rank}.npz"),
+            F=F, J_data=J.data, J_indices=part.verts[J.indices], J_indptr=J.indptr,
+            A_data=A.data, A_indices=part.verts[A.indices], A_indptr=A.indptr,
+            b=b[g0 : g0 + part.n_owned], lo=part.bounds[rank], hi=part.bounds[rank + 1],
+        )
+        # one all-reduce of a double: the distributed ||F||^2
+        t = torch.tensor([float(numpy.dot(F, F))], dtype=torch.float64)
+        dist.all_reduce(t)
+        if rank == 0:
+            numpy.save(os.path.join(out_dir, "normsq.npy"), t.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def gpu_worker():
+    """Launched by torchrun on a multi-GPU box: every rank runs its partition on its
+    GPU with both halo back ends; rank 0 compares the gathered result with the
+    single-GPU engine bit for bit."""
+    import torch
+    import torch.distributed as dist
+
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import dist as fd
+    from tests import problems
+
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    try:
+        for kind, n, pname in (("rect", 67, "nonlinear_conv"), ("cube", 15, "bratu")):
+            mesh = _mesh(kind, n)
+            nglob = len(mesh.points)
+            part = fd.Partition(mesh, rank, world)
+            prob = getattr(problems, pname)(eng.form_language)
+            rng = numpy.random.default_rng(3)
+            us = [0.3 * rng.standard_normal(nglob) for _ in range(3)]
+            results = {}
+            for halo in ("peer", "torch"):
+                dp = fd.DistributedFvm(prob, part, halo=halo)
+                Fs, Js = [], []
+                for u in us:  # several epochs: exercises the double buffering
+                    Fs.append(dp.eval(part.owned(u)))
+                    Js.append(dp.jacobian_values(part.owned(u)))
+                results[halo] = (Fs, Js)
+                if halo == "peer":
+                    dist.barrier()
+                    dp.halo.close()
+            A_loc, b_loc = fd.discretize_linear(
+                problems.convection_diffusion(eng.form_language), part
+            )
+            gathered = [None] * world
+            payload = {
+                h: ([f.tobytes() for f in r[0]], [j.data.tobytes() for j in r[1]],
+                    [j.indices.tobytes() for j in r[1]])
+                for h, r in results.items()
+            }
+            payload["lin"] = (A_loc.data.tobytes(), A_loc.indices.tobytes(), b_loc.tobytes())
+            dist.all_gather_object(gathered, payload)
+            if rank == 0:
+                f1, j1 = eng.discretize(prob, mesh)
+                A1, b1 = eng.discretize_linear(problems.convection_diffusion(eng.form_language), mesh)
+                for h in ("peer", "torch"):
+                    for k, u in enumerate(us):
+                        F = b"".join(g[h][0][k] for g in gathered)
+                        Jd = b"".join(g[h][1][k] for g in gathered)
+                        Ji = b"".join(g[h][2][k] for g in gathered)
+                        J1 = j1.get_linear_operator(u)
+                        same = (
+                            F == f1.eval(u).tobytes()
+                            and Jd == J1.data.tobytes()
+                            and Ji == J1.indices.tobytes()
+                        )
+                        print(f"{kind} {pname} halo={h} u{k}: bit-identical={same}", flush=True)
+                        ok &= same
+                lin = (
+                    b"".join(g["lin"][0] for g in gathered) == A1.data.tobytes()
+                    and b"".join(g["lin"][1] for g in gathered) == A1.indices.tobytes()
+                    and b"".join(g["lin"][2] for g in gathered) == b1.tobytes()
+                )
+                print(f"{kind} linear assembly: bit-identical={lin}", flush=True)
+                ok &= lin
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.broadcast(flag, 0)
+        ok = bool(flag.item())
+    finally:
+        dist.destroy_process_group()
+    if rank == 0:
+        print("DIST_GPU_OK" if ok else "DIST_GPU_FAILED", flush=True)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    gpu_worker()
