@@ -124,35 +124,30 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def slab(nx, ny, rank, world):
-    """Grid rows [j0, j1) owned by ``rank`` and the local sub-grid (one ghost grid
-    row on each interior side).  Local vertex numbering is the global one
-    shifted by ``g0 * nx`` (monotone), so per-row fold order equals the 1-GPU run."""
-    j0 = (ny * rank) // world
-    j1 = (ny * (rank + 1)) // world
-    g0 = max(j0 - 1, 0)
-    g1 = min(j1 + 1, ny)
-    return j0, j1, g0, g1
-
-
-def build_local_problem(size, rank, world, lx=1.0, ly=1.0):
+def build_local_problem(size, rank, world):
+    """This rank's slab of the size x size grid (generated locally; the ghost grid
+    rows hold every cell that touches an owned vertex) and its linear problem."""
     import pyfvm_b200 as eng
-    from pyfvm_b200 import meshes, problem
+    from pyfvm_b200 import dist as fd
+    from pyfvm_b200 import problem
 
-    nx = ny = size
-    xs = numpy.linspace(0.0, lx, nx)
-    ys = numpy.linspace(0.0, ly, ny)
-    j0, j1, g0, g1 = slab(nx, ny, rank, world)
-    v, c = meshes.rectangle_tri(xs, ys[g0:g1], parity=g0)
-    mesh = meshes.Mesh(v, c)
-    if world > 1:
-        # ghost grid rows are not domain boundary; the true boundary is known analytically
-        gj = numpy.arange(g0, g1).repeat(nx)
-        gi = numpy.tile(numpy.arange(nx), g1 - g0)
-        mesh._boundary = (gi == 0) | (gi == nx - 1) | (gj == 0) | (gj == ny - 1)
-    row_range = ((j0 - g0) * nx, (j1 - j0) * nx)
-    lp = problem.LinearProblem(problem_c4(eng.form_language), mesh, row_range=row_range)
-    return mesh, lp
+    xs = numpy.linspace(0.0, 1.0, size)
+    part = fd.SlabPartition([xs, xs], rank, world)
+    lp = problem.LinearProblem(problem_c4(eng.form_language), part.mesh, row_range=part.row_range)
+    return part, lp
+
+
+def measured_traffic(size, quantum):
+    """DRAM bytes per assembly launch from the committed ncu capture
+    (profiles/r01_traffic.json), if it was taken on this workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        if int(t["size"]) == size and int(t["tile_quantum"]) == quantum:
+            return int(t["assembly_dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
 
 
 def run_ours(args):
@@ -174,7 +169,8 @@ def run_ours(args):
     from pyfvm_b200 import codegen
 
     t_setup = time.time()
-    mesh, lp = build_local_problem(args.size, rank, world)
+    part, lp = build_local_problem(args.size, rank, world)
+    mesh = part.mesh
     eng = lp.eng
     dm = lp.dmesh
     n_rows, nnz = dm.n_rows, dm.nnz
@@ -182,6 +178,7 @@ def run_ours(args):
     # contributions this rank processes: half-edges / 2 (cut records count once per side)
     R_local = dm.n_halfedges / 2.0
     setup_s = time.time() - t_setup
+    quantum = dm.stats()["quantum"]
 
     sampler = ClockSampler(local)
     # ---- device-resident timing: K launches between CUDA events on the ctx stream
@@ -201,9 +198,12 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop(t0, t1)
 
-    # ---- end to end through the plugin API with host buffers: per step the
-    # per-record geometry goes host -> device (pinned), is permuted into
-    # half-edge order, assembled, and the CSR values + rhs come back to the host
+    # ---- end to end through the plugin objects with HOST buffers.  Per step the
+    # per-record geometry goes host -> device (pinned), is permuted into half-edge
+    # order and assembled, and the CSR values + rhs come back to pinned host
+    # arrays.  The device -> host copy runs on the copy stream, so it overlaps the
+    # next step's upload (PCIe is full duplex); the fence keeps a buffer from being
+    # rewritten while it is still being read.
     ce_host = eng.pinned_empty(dm.R, numpy.float64)
     ce_host[:] = numpy.asarray(mesh.ce_ratios).reshape(-1)
     data_host = eng.pinned_empty(nnz, numpy.float64)
@@ -211,53 +211,105 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 10))
     for i in range(2 + e2e_steps):
         if i == 2:
+            eng.copy_sync()
             eng.sync()
             barrier()
             te = time.time()
         lp.update_geometry(ce=ce_host)
+        eng.copy_fence()
         lp.assemble_device()
-        lp.data.download(data_host)
-        lp.vec.download(rhs_host)
+        lp.data.download_async(data_host)
+        lp.vec.download_async(rhs_host)
+    eng.copy_sync()
     e2e_s = (time.time() - te) / e2e_steps
     barrier()
 
-    # ---- residual evaluation on the same mesh (config 4: "linear assembly + residual eval")
-    res = None
-    if world == 1:
+    peak, peak_src = measured_peak()
+    # ---- cold call: pyfvm.discretize_linear(problem, mesh) on a mesh the engine has
+    # not seen (upload of the whole mesh, on-device pattern build, assembly, pattern +
+    # values back to the host); the functor set is already compiled
+    cold = None
+    if world == 1 and not args.no_cold:
         import pyfvm_b200 as pe
+        from pyfvm_b200 import engine as pengine
 
-        f, jac = pe.discretize(problem_c4(pe.form_language), mesh)
-        u = numpy.random.default_rng(0).standard_normal(len(mesh.points))
-        s = f._s
-        s.upload_u(u)
+        pengine._mesh_cache.clear()
+        eng.sync()
+        tc = time.time()
+        A_cold, b_cold = pe.discretize_linear(problem_c4(pe.form_language), mesh)
+        cold_s = time.time() - tc
+        cold = {
+            "seconds": cold_s,
+            "value": R_global / cold_s,
+            "unit": UNIT,
+            "what": "pyfvm.discretize_linear(problem, mesh) on an uncached mesh: sympy lowering, "
+            "int64 index + geometry upload from pageable numpy arrays, on-device pattern build, "
+            "assembly, indptr/indices/values/rhs back to the host",
+        }
+        del A_cold, b_cold
+        pengine._mesh_cache.clear()
+
+    # ---- residual evaluation on the same mesh (config 4: "linear assembly + residual
+    # eval").  N > 1: rows partitioned the same way, ghost values of u pushed over
+    # NVLink peer memory before every evaluation (included in the time).
+    from pyfvm_b200 import dist as fd
+    import pyfvm_b200 as pe
+
+    res = None
+    u_glob = None
+    if not args.no_residual:
+        dp = fd.DistributedFvm(problem_c4(pe.form_language), part, halo="peer") if world > 1 else None
+        if world == 1:
+            f, jac = pe.discretize(problem_c4(pe.form_language), mesh)
+            s = f._s
+            s.upload_u(numpy.random.default_rng(0).standard_normal(part.n_local))
+            step = lambda: f.eval_device(s.u.ptr)
+        else:
+            rng = numpy.random.default_rng(rank)
+            s = dp.s
+
+            def step():
+                # the owned part of the next u is already on the device (Newton's
+                # update would have written it); push / wait / evaluate
+                dp.residual_device(dp.exchange())
+
+            for k in (0, 1):
+                dp.set_owned(rng.standard_normal(part.n_owned))
+                step()
         for _ in range(args.warmup):
-            f.eval_device(s.u.ptr)
+            step()
+        eng.sync()
+        barrier()
         eng.timer_begin()
         for _ in range(args.steps):
-            f.eval_device(s.u.ptr)
+            step()
         rms = eng.timer_end() / args.steps
+        barrier()
+        if dp is not None:
+            dp.halo.check_timeout()
         fun = s.functors[codegen.MODE_RESIDUAL]
-        rb = algorithmic_bytes(dm.R, nnz, n_rows, dm.dim, True, fun.uses_el, "residual")
-        peak, _ = measured_peak()
-        res = {
-            "ms_per_eval": rms,
-            "contributions_per_s": dm.R / (rms * 1e-3),
-            "algorithmic_bytes": rb,
-            "achieved_gbs": rb / (rms * 1e-3) / 1e9,
-            "frac": rb / (rms * 1e-3) / 1e9 / peak,
-        }
+        rb = algorithmic_bytes(R_local, nnz, n_rows, dm.dim, True, fun.uses_el, "residual")
+        res = {"ms_per_eval": rms, "algorithmic_bytes": int(rb)}
 
     # ---- reduce over ranks: max time, summed work
     ms_step = ms / args.steps
     if dist is not None:
         import torch
 
-        t = torch.tensor([ms_step, e2e_s], device="cuda", dtype=torch.float64)
+        rms_local = res["ms_per_eval"] if res else 0.0
+        t = torch.tensor([ms_step, e2e_s, rms_local], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_s = t.tolist()
+        ms_step, e2e_s, rms_max = t.tolist()
+        if res:
+            res["ms_per_eval"] = rms_max
+            res["halo"] = "CUDA-IPC peer push over NVLink + epoch flags, inside the timed region"
+    if res:
+        rms = res["ms_per_eval"]
+        res["contributions_per_s"] = R_global / (rms * 1e-3)
+        res["achieved_gbs_per_gpu"] = res["algorithmic_bytes"] / (rms * 1e-3) / 1e9
+        res["frac"] = res["achieved_gbs_per_gpu"] / peak
 
     fun = lp.functors[codegen.MODE_LINEAR]
-    peak, peak_src = measured_peak()
     alg = algorithmic_bytes(R_local, nnz, n_rows, dm.dim, True, fun.uses_el, "assembly")
     out = {
         "metric": METRIC,
@@ -279,7 +331,7 @@ def run_ours(args):
             "l2": "inputs larger than L2 (no flush needed)"
             if alg > 4 * 126e6
             else "working set may fit in L2",
-            "tile_quantum": int(os.environ.get("FVM_TILE_QUANTUM", "2432")),
+            "tile_quantum": quantum,
         },
         "gpu_launches": launches,
         "clocks": clocks,
@@ -289,7 +341,8 @@ def run_ours(args):
             "h2d_bytes_per_step": int(8 * dm.R),
             "d2h_bytes_per_step": int(8 * nnz + 8 * n_rows),
             "what": "per step: ce_ratios host->device (pinned) + permute to half-edge order + "
-            "assembly + CSR values and rhs device->host; pattern cached per mesh",
+            "assembly + CSR values and rhs device->host (pinned, copy stream: overlaps the next "
+            "step's upload); pattern cached per mesh",
         },
         "roofline": {
             "bound": "hbm",
@@ -297,13 +350,14 @@ def run_ours(args):
             "peak": peak,
             "unit": "GB/s",
             "frac": alg / (ms_step * 1e-3) / 1e9 / peak,
-            "traffic": None,
+            "traffic": measured_traffic(args.size, quantum) if world == 1 else None,
             "kernel": "fvm_tile_kernel (mode linear)",
             "algorithmic_bytes_per_launch": int(alg),
             "peak_source": peak_src,
             "frac_of_8TBs_nominal": alg / (ms_step * 1e-3) / 8e12,
         },
         "residual": res,
+        "e2e_cold": cold,
         "pattern_build_ms": dm.build_ms,
         "setup_s": setup_s,
     }
@@ -405,6 +459,8 @@ def main():
     ap.add_argument("--size", type=int, default=4001, help="grid points per side")
     ap.add_argument("--cpu-size", type=int, default=2001, help="side of the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cold", action="store_true", help="skip the cold discretize_linear call")
+    ap.add_argument("--no-residual", action="store_true", help="skip the residual leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -72,6 +72,15 @@ int fvm_dev_free(fvm_ctx* ctx, void* ptr_dev);
 int fvm_dev_memset(fvm_ctx* ctx, void* ptr_dev, int value, size_t bytes);
 int fvm_h2d(fvm_ctx* ctx, void* dst_dev, const void* src, size_t bytes);
 int fvm_d2h(fvm_ctx* ctx, void* dst, const void* src_dev, size_t bytes);
+/* device -> pinned host copy on the ctx's copy stream, ordered after the work issued
+ * so far on the ctx stream; it overlaps whatever the ctx stream does next (e.g.
+ * the next step's host -> device upload: PCIe is full duplex) */
+int fvm_d2h_async(fvm_ctx* ctx, void* dst_pinned, const void* src_dev, size_t bytes);
+/* later work on the ctx stream waits for the copies issued so far (call it before
+ * overwriting a buffer an async copy is still reading) */
+int fvm_copy_fence(fvm_ctx* ctx);
+/* host waits for the copies issued so far */
+int fvm_copy_sync(fvm_ctx* ctx);
 int fvm_host_alloc(fvm_ctx* ctx, size_t bytes, void** out); /* pinned */
 int fvm_host_free(fvm_ctx* ctx, void* ptr);
 

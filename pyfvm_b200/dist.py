@@ -138,6 +138,68 @@ class Partition:
         return numpy.ascontiguousarray(x_global[lo:hi])
 
 
+class SlabPartition:
+    """Rank ``rank``'s slab of a structured ``rectangle_tri`` (2-D) or
+    ``cube_tetra`` (3-D) grid, generated locally: the global mesh is never
+    materialised, so the largest configurations only ever exist in pieces.
+
+    The slowest grid axis is cut; a slab carries one ghost grid layer on each
+    interior side, which holds every cell that touches an owned vertex.  Same
+    fields as :class:`Partition` (local numbering = global numbering shifted by
+    the first local vertex: monotone)."""
+
+    def __init__(self, axes, rank, world):
+        from . import meshes
+
+        axes = [numpy.asarray(a, dtype=numpy.float64) for a in axes]
+        dim = len(axes)
+        assert dim in (2, 3)
+        nslow = len(axes[-1])
+        layer = int(numpy.prod([len(a) for a in axes[:-1]]))  # vertices per grid layer
+        cuts = [(nslow * r) // world for r in range(world + 1)]
+        assert all(cuts[r + 1] > cuts[r] for r in range(world)), "more ranks than grid layers"
+        j0, j1 = cuts[rank], cuts[rank + 1]
+        g0, g1 = max(j0 - 1, 0), min(j1 + 1, nslow)
+        self.rank, self.world = rank, world
+        self.n_global = layer * nslow
+        self.bounds = [c * layer for c in cuts]
+        if dim == 2:
+            pts, cells = meshes.rectangle_tri(axes[0], axes[1][g0:g1], parity=g0)
+        else:
+            pts, cells = meshes.cube_tetra(axes[0], axes[1], axes[2][g0:g1], parity=g0)
+        mesh = meshes.Mesh(pts, cells)
+        # ghost layers are not domain boundary; the true boundary is known analytically
+        nloc = len(pts)
+        lid = numpy.arange(nloc)
+        on = numpy.zeros(nloc, dtype=bool)
+        stride = 1
+        for a in axes[:-1]:
+            k = (lid // stride) % len(a)
+            on |= (k == 0) | (k == len(a) - 1)
+            stride *= len(a)
+        ks = lid // layer + g0
+        on |= (ks == 0) | (ks == nslow - 1)
+        mesh._boundary = on
+        self.mesh = mesh
+        self.n_local = nloc
+        self.n_ghost_lo = (j0 - g0) * layer
+        self.n_owned = (j1 - j0) * layer
+        self.row_range = (self.n_ghost_lo, self.n_owned)
+        self.verts = numpy.arange(g0 * layer, g1 * layer)
+        self.recv, self.send = {}, {}
+        if j0 > g0:  # ghost layer below: owned by rank - 1; it needs my first layer
+            self.recv[rank - 1] = (0, layer)
+            self.send[rank - 1] = numpy.arange(self.n_ghost_lo, self.n_ghost_lo + layer, dtype=numpy.int32)
+        if g1 > j1:
+            self.recv[rank + 1] = (self.n_ghost_lo + self.n_owned, layer)
+            first = self.n_ghost_lo + self.n_owned - layer
+            self.send[rank + 1] = numpy.arange(first, first + layer, dtype=numpy.int32)
+        self.neighbours = sorted(self.recv)
+
+    def owned(self, x_global):
+        return numpy.ascontiguousarray(x_global[self.bounds[self.rank] : self.bounds[self.rank + 1]])
+
+
 # ---------------------------------------------------------------------------
 # halo exchange back ends
 # ---------------------------------------------------------------------------

@@ -69,6 +69,9 @@ SYMBOLS = {
     "fvm_dev_memset": (c_int, [c_void_p, c_void_p, c_int, c_size_t]),
     "fvm_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "fvm_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "fvm_d2h_async": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "fvm_copy_fence": (c_int, [c_void_p]),
+    "fvm_copy_sync": (c_int, [c_void_p]),
     "fvm_host_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "fvm_host_free": (c_int, [c_void_p, c_void_p]),
     "fvm_timer_begin": (c_int, [c_void_p]),
@@ -166,6 +169,15 @@ class DeviceBuffer:
         self.eng._ck(self.eng.lib.fvm_d2h(self.eng.ctx, _ptr(out), self.ptr, out.nbytes))
         return out
 
+    def download_async(self, out_pinned):
+        """Copy to a pinned host array on the copy stream (``Engine.copy_sync``
+        completes it; ``Engine.copy_fence`` before the buffer is rewritten)."""
+        assert out_pinned.flags["C_CONTIGUOUS"] and out_pinned.nbytes <= self.nbytes
+        self.eng._ck(
+            self.eng.lib.fvm_d2h_async(self.eng.ctx, _ptr(out_pinned), self.ptr, out_pinned.nbytes)
+        )
+        return out_pinned
+
 
 class Engine:
     """One device context (= one CUDA stream on one GPU) plus the compiled
@@ -225,6 +237,12 @@ class Engine:
 
     def sync(self):
         self._ck(self.lib.fvm_ctx_sync(self.ctx))
+
+    def copy_fence(self):
+        self._ck(self.lib.fvm_copy_fence(self.ctx))
+
+    def copy_sync(self):
+        self._ck(self.lib.fvm_copy_sync(self.ctx))
 
     def timer_begin(self):
         self._ck(self.lib.fvm_timer_begin(self.ctx))

@@ -200,9 +200,11 @@ def rectangle_tri(xs, ys, parity=0):
     return points, cells
 
 
-def cube_tetra(xs, ys, zs):
+def cube_tetra(xs, ys, zs, parity=0):
     """``meshzoo.cube_tetra``-style tensor grid, every hexahedron split into 5
-    tetrahedra with alternating orientation (conforming)."""
+    tetrahedra with alternating orientation (conforming).
+    ``parity`` shifts the alternation so that a slab ``zs[g0:g1]`` of a larger
+    grid reproduces the global cells."""
     xs, ys, zs = (numpy.asarray(a, dtype=numpy.float64) for a in (xs, ys, zs))
     nx, ny, nz = len(xs), len(ys), len(zs)
     Z, Y, X = numpy.meshgrid(zs, ys, xs, indexing="ij")
@@ -216,7 +218,7 @@ def cube_tetra(xs, ys, zs):
         return ((iz + dz) * ny + (iy + dy)) * nx + (ix + dx)
 
     v = {(dx, dy, dz): vid(dx, dy, dz) for dx in (0, 1) for dy in (0, 1) for dz in (0, 1)}
-    even = (ix + iy + iz) % 2 == 0
+    even = (ix + iy + iz + parity) % 2 == 0
     # even cubes: corner tets at 000,110,101,011 cut off; centre tet joins the rest
     split_even = [
         [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)],

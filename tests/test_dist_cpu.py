@@ -78,3 +78,47 @@ def test_gloo_halo_and_owned_rows(kind, n, world, tmp_path):
             assert z[f"{name}_data"].tobytes() == blk.data.tobytes()
     normsq = numpy.load(os.path.join(tmp_path, "normsq.npy"))[0]
     assert normsq == pytest.approx(float(F @ F), rel=1e-14)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_slab_partition_matches_general_partition(dim, world):
+    """Slabs generated locally (the global mesh never exists) hold exactly the
+    records, control volumes, boundary flags and halo links of the general
+    partition of the global mesh."""
+    from pyfvm_b200 import dist as fd
+    from pyfvm_b200 import meshes
+
+    if dim == 2:
+        axes = [numpy.linspace(0, 1, 7), numpy.linspace(0, 2, 9)]
+        gm = meshes.Mesh(*meshes.rectangle_tri(*axes))
+    else:
+        axes = [numpy.linspace(0, 1, 7), numpy.linspace(0, 2, 6), numpy.linspace(0, 1, 9)]
+        gm = meshes.Mesh(*meshes.cube_tetra(*axes))
+
+    def records(part):
+        idx = part.mesh.idx_hierarchy.reshape(2, -1)
+        ce = numpy.asarray(part.mesh.ce_ratios).reshape(-1)
+        g0, g1 = part.verts[idx[0]], part.verts[idx[1]]
+        lo, hi = part.bounds[part.rank], part.bounds[part.rank + 1]
+        keep = ((g0 >= lo) & (g0 < hi)) | ((g1 >= lo) & (g1 < hi))
+        a, c = numpy.stack([g0[keep], g1[keep]], 1), ce[keep]
+        o = numpy.lexsort((c, a[:, 1], a[:, 0]))
+        return a[o], c[o]
+
+    for r in range(world):
+        sp = fd.SlabPartition(axes, r, world)
+        gp = fd.Partition(gm, r, world, bounds=sp.bounds)
+        (a1, c1), (a2, c2) = records(sp), records(gp)
+        assert numpy.array_equal(a1, a2)
+        assert numpy.allclose(c1, c2, rtol=1e-12, atol=1e-15)
+        g0, lo, hi = sp.n_ghost_lo, sp.bounds[r], sp.bounds[r + 1]
+        assert numpy.allclose(
+            sp.mesh.control_volumes[g0 : g0 + sp.n_owned], gm.control_volumes[lo:hi], rtol=1e-13
+        )
+        assert numpy.array_equal(
+            sp.mesh.is_boundary_point[g0 : g0 + sp.n_owned], gm.is_boundary_point[lo:hi]
+        )
+        for q, (start, count) in sp.recv.items():
+            sq = fd.SlabPartition(axes, q, world)
+            assert numpy.array_equal(sp.verts[start : start + count], sq.verts[sq.send[r]])
