@@ -110,8 +110,10 @@ typedef struct fvm_mesh_desc {
   const uint8_t* rec_mask;  /* [n_records] edge-term subdomain bits, may be NULL
                                (records with mask 0 are left out of the pattern) */
   const double* coords;     /* [n_vertices*dim] row-major                       */
-  const double* control_volumes; /* [n_vertices]                               */
+  const double* control_volumes; /* [n_vertices]; NULL: derived on the device for the
+                               owned rows (needs edge_len), as sum |e|^2 ce / (2 cell_dim) */
   int32_t tile_quantum; /* 0 = default; half-edges+slots per tile              */
+  int32_t cell_dim;     /* 2 triangles, 3 tetrahedra (used when control_volumes == NULL) */
 } fvm_mesh_desc;
 
 int fvm_mesh_create(fvm_ctx* ctx, const fvm_mesh_desc* desc, fvm_mesh** out);
@@ -126,7 +128,7 @@ int fvm_mesh_info(fvm_mesh* mesh, int64_t* nnz, int64_t* n_halfedges, int32_t* n
 int fvm_mesh_stats(fvm_mesh* mesh, int64_t* out, int n);
 /* copy an internal layout array to the host for inspection / tests:
  * 0 = tile descriptors (128 B each), 1 = packed slot metadata (4 B per slot),
- * 2 = ce_ratios in half-edge order (8 B per half-edge) */
+ * 2 = ce_ratios in half-edge order (8 B per half-edge), 3 = control volumes */
 int fvm_mesh_debug_copy(fvm_mesh* mesh, int which, void* out, size_t bytes);
 /* CSR pattern to host: indptr[n_rows+1], indices[nnz] (local vertex ids) */
 int fvm_mesh_get_pattern(fvm_mesh* mesh, int32_t* indptr, int32_t* indices);
@@ -135,6 +137,29 @@ int fvm_mesh_pattern_dev(fvm_mesh* mesh, const int32_t** indptr_dev, const int32
 /* re-upload per-record geometry (same connectivity), permuted on the device */
 int fvm_mesh_update_geometry(fvm_mesh* mesh, const double* ce_ratios, const double* edge_len,
                              const double* coords, const double* control_volumes, int on_device);
+
+/* ---- mesh generation and geometry on the device (the step before the
+ * path).  meshplex derives idx_hierarchy / ce_ratios / ei_dot_ei / control_volumes
+ * with numpy on the host; for the largest meshes the per-record arrays only ever
+ * exist in HBM.  Record order = meshplex's idx_hierarchy flattened: triangles
+ * record = k*cells + c, tetrahedra record = (j*4 + k)*cells + c.
+ * Generators reproduce meshzoo.rectangle_tri / cube_tetra [README.md:44-46] (x fastest;
+ * `parity` shifts the zigzag so a slab of a larger grid reproduces the global cells);
+ * xs/ys/zs are HOST axis arrays, outputs are caller-allocated device arrays:
+ * points [n*2 | n*3], cells [2(nx-1)(ny-1)*3 | 5(nx-1)(ny-1)(nz-1)*4]. */
+int fvm_gen_rectangle_tri(fvm_ctx* ctx, int nx, int ny, int parity, const double* xs,
+                          const double* ys, int index_bytes, double* points_dev, void* cells_dev);
+int fvm_gen_cube_tetra(fvm_ctx* ctx, int nx, int ny, int nz, int parity, const double* xs,
+                       const double* ys, const double* zs, int index_bytes, double* points_dev,
+                       void* cells_dev);
+/* per-record endpoints, ce_ratios and edge lengths of n_cells simplices (device in,
+ * device out; R = 3*n_cells or 12*n_cells records; el_dev may be NULL) */
+int fvm_geometry(fvm_ctx* ctx, int cell_dim, int coord_dim, int64_t n_cells, const void* cells_dev,
+                 int index_bytes, const double* points_dev, void* idx0_dev, void* idx1_dev,
+                 double* ce_dev, double* el_dev);
+/* triangle meshes: out_dev[v] = 1 for owned vertices on a boundary edge (an edge that
+ * belongs to exactly one cell), from the pattern's half-edge counts */
+int fvm_mesh_boundary_tri(fvm_mesh* mesh, uint8_t* out_dev);
 
 /* ---- functor compilation (NVRTC -> sm_100a cubin) ---------------------------
  * Replaces sympy.lambdify in the reference's discretize step: functor_src is

@@ -54,6 +54,7 @@ class LocalMesh:
         self._rec_global = rec_global
         self._cell_of_record = cell_of_record
         self._parent = parent
+        self.cell_dim = getattr(parent, "cell_dim", 3 if numpy.asarray(parent.idx_hierarchy).ndim == 4 else 2)
 
     def get_vertex_mask(self, subdomain=None):
         if subdomain is None:
@@ -148,7 +149,9 @@ class SlabPartition:
     fields as :class:`Partition` (local numbering = global numbering shifted by
     the first local vertex: monotone)."""
 
-    def __init__(self, axes, rank, world):
+    def __init__(self, axes, rank, world, device=False):
+        """``device=True``: points, cells and geometry of the slab are generated in
+        HBM (``pyfvm_b200.device_meshes``); nothing per-record exists on the host."""
         from . import meshes
 
         axes = [numpy.asarray(a, dtype=numpy.float64) for a in axes]
@@ -163,13 +166,8 @@ class SlabPartition:
         self.rank, self.world = rank, world
         self.n_global = layer * nslow
         self.bounds = [c * layer for c in cuts]
-        if dim == 2:
-            pts, cells = meshes.rectangle_tri(axes[0], axes[1][g0:g1], parity=g0)
-        else:
-            pts, cells = meshes.cube_tetra(axes[0], axes[1], axes[2][g0:g1], parity=g0)
-        mesh = meshes.Mesh(pts, cells)
         # ghost layers are not domain boundary; the true boundary is known analytically
-        nloc = len(pts)
+        nloc = layer * (g1 - g0)
         lid = numpy.arange(nloc)
         on = numpy.zeros(nloc, dtype=bool)
         stride = 1
@@ -179,7 +177,20 @@ class SlabPartition:
             stride *= len(a)
         ks = lid // layer + g0
         on |= (ks == 0) | (ks == nslow - 1)
-        mesh._boundary = on
+        if device:
+            from . import device_meshes as dm
+
+            if dim == 2:
+                mesh = dm.device_rectangle_tri(axes[0], axes[1][g0:g1], parity=g0, boundary=on)
+            else:
+                mesh = dm.device_cube_tetra(axes[0], axes[1], axes[2][g0:g1], parity=g0, boundary=on)
+        else:
+            if dim == 2:
+                pts, cells = meshes.rectangle_tri(axes[0], axes[1][g0:g1], parity=g0)
+            else:
+                pts, cells = meshes.cube_tetra(axes[0], axes[1], axes[2][g0:g1], parity=g0)
+            mesh = meshes.Mesh(pts, cells)
+            mesh._boundary = on
         self.mesh = mesh
         self.n_local = nloc
         self.n_ghost_lo = (j0 - g0) * layer

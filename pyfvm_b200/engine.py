@@ -40,6 +40,7 @@ class MeshDesc(ctypes.Structure):
         ("coords", c_void_p),
         ("control_volumes", c_void_p),
         ("tile_quantum", c_int32),
+        ("cell_dim", c_int32),
     ]
 
 
@@ -87,6 +88,18 @@ SYMBOLS = {
     "fvm_mesh_get_pattern": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fvm_mesh_pattern_dev": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
     "fvm_mesh_update_geometry": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "fvm_gen_rectangle_tri": (
+        c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    ),
+    "fvm_gen_cube_tetra": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    ),
+    "fvm_geometry": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "fvm_mesh_boundary_tri": (c_int, [c_void_p, c_void_p]),
     "fvm_kernel_create": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_void_p)]),
     "fvm_kernel_launch_shape": (
         c_int,
@@ -309,15 +322,22 @@ class Kernel:
 
 
 def _mesh_arrays(mesh):
-    """Read the meshplex attribute contract once."""
-    idx = numpy.asarray(mesh.idx_hierarchy)
+    """Vertex coordinates of a mesh object and the number of
+    coordinate columns the functors see."""
     coords = numpy.asarray(
         mesh.node_coords if hasattr(mesh, "node_coords") else mesh.points, dtype=numpy.float64
     )
     dim = coords.shape[1]
     if dim == 3 and not numpy.any(coords[:, 2]):
         dim = 2  # planar mesh carried with a zero third column
-    return idx, coords, dim
+    return coords, dim
+
+
+def _cell_dim(mesh):
+    if hasattr(mesh, "cell_dim"):
+        return int(mesh.cell_dim)
+    idx = numpy.asarray(mesh.idx_hierarchy)
+    return 3 if idx.ndim == 4 else 2  # (2, 3, cells) / (2, 3, 4, cells); flat lists: triangles
 
 
 class DeviceMesh:
@@ -328,48 +348,59 @@ class DeviceMesh:
     def __init__(self, eng, mesh, rec_mask=None, need_el=True, row_range=None, tile_quantum=0):
         tile_quantum = tile_quantum or int(os.environ.get("FVM_TILE_QUANTUM", "0"))
         self.eng = eng
-        idx, coords, dim = _mesh_arrays(mesh)
+        coords, dim = _mesh_arrays(mesh)
         self.dim = dim
         self.n = coords.shape[0]
-        idx0 = numpy.ascontiguousarray(idx[0].reshape(-1))
-        idx1 = numpy.ascontiguousarray(idx[1].reshape(-1))
-        if idx0.dtype not in (numpy.int32, numpy.int64):
-            idx0, idx1 = idx0.astype(numpy.int64), idx1.astype(numpy.int64)
-        ce = numpy.ascontiguousarray(numpy.asarray(mesh.ce_ratios, dtype=numpy.float64).reshape(-1))
-        el = None
-        if need_el:
-            el = numpy.sqrt(numpy.asarray(mesh.ei_dot_ei, dtype=numpy.float64)).reshape(-1)
-            el = numpy.ascontiguousarray(el)
-        xy = numpy.ascontiguousarray(coords[:, :dim])
-        cv = numpy.ascontiguousarray(numpy.asarray(mesh.control_volumes, dtype=numpy.float64))
-        if rec_mask is not None:
-            rec_mask = numpy.ascontiguousarray(rec_mask, dtype=numpy.uint8)
-            assert rec_mask.shape == idx0.shape
-        self.R = idx0.shape[0]
         row_base, n_rows = (0, self.n) if row_range is None else row_range
         self.row_base, self.n_rows = row_base, n_rows
-        d = MeshDesc(
-            dim=dim,
-            n_vertices=self.n,
-            row_base=row_base,
-            n_rows=n_rows,
-            n_records=self.R,
-            index_bytes=idx0.dtype.itemsize,
-            on_device=0,
-            idx0=_ptr(idx0),
-            idx1=_ptr(idx1),
-            ce_ratios=_ptr(ce),
-            edge_len=_ptr(el),
-            rec_mask=_ptr(rec_mask),
-            coords=_ptr(xy),
-            control_volumes=_ptr(cv),
-            tile_quantum=tile_quantum,
-        )
+        if rec_mask is not None:
+            rec_mask = numpy.ascontiguousarray(rec_mask, dtype=numpy.uint8)
+        if hasattr(mesh, "device_records"):
+            # per-record arrays already live in HBM (pyfvm_b200.device_meshes)
+            rec = mesh.device_records(eng, need_el=True)
+            self.R = rec["n_records"]
+            keep = [rec]  # keeps the device buffers alive until the mesh is built
+            xy = eng.to_device(numpy.ascontiguousarray(coords[:, :dim]))
+            mask_dev = eng.to_device(rec_mask) if rec_mask is not None else None
+            assert rec_mask is None or rec_mask.shape == (self.R,)
+            d = MeshDesc(
+                dim=dim, n_vertices=self.n, row_base=row_base, n_rows=n_rows, n_records=self.R,
+                index_bytes=rec["index_bytes"], on_device=1, idx0=rec["idx0"], idx1=rec["idx1"],
+                ce_ratios=rec["ce"], edge_len=rec["el"],
+                rec_mask=None if mask_dev is None else mask_dev.ptr, coords=xy.ptr,
+                control_volumes=None, tile_quantum=tile_quantum, cell_dim=_cell_dim(mesh),
+            )
+            el = True
+        else:
+            idx = numpy.asarray(mesh.idx_hierarchy)
+            idx0 = numpy.ascontiguousarray(idx[0].reshape(-1))
+            idx1 = numpy.ascontiguousarray(idx[1].reshape(-1))
+            if idx0.dtype not in (numpy.int32, numpy.int64):
+                idx0, idx1 = idx0.astype(numpy.int64), idx1.astype(numpy.int64)
+            ce = numpy.ascontiguousarray(
+                numpy.asarray(mesh.ce_ratios, dtype=numpy.float64).reshape(-1)
+            )
+            el = None
+            if need_el:
+                el = numpy.sqrt(numpy.asarray(mesh.ei_dot_ei, dtype=numpy.float64)).reshape(-1)
+                el = numpy.ascontiguousarray(el)
+            xy = numpy.ascontiguousarray(coords[:, :dim])
+            cv = numpy.ascontiguousarray(numpy.asarray(mesh.control_volumes, dtype=numpy.float64))
+            assert rec_mask is None or rec_mask.shape == idx0.shape
+            self.R = idx0.shape[0]
+            d = MeshDesc(
+                dim=dim, n_vertices=self.n, row_base=row_base, n_rows=n_rows, n_records=self.R,
+                index_bytes=idx0.dtype.itemsize, on_device=0, idx0=_ptr(idx0), idx1=_ptr(idx1),
+                ce_ratios=_ptr(ce), edge_len=_ptr(el), rec_mask=_ptr(rec_mask), coords=_ptr(xy),
+                control_volumes=_ptr(cv), tile_quantum=tile_quantum, cell_dim=_cell_dim(mesh),
+            )
         h = c_void_p()
         eng._ck(eng.lib.fvm_mesh_create(eng.ctx, byref(d), byref(h)))
         self.handle = h
         self._fin = weakref.finalize(self, eng.lib.fvm_mesh_destroy, h)
         self.has_el = el is not None
+        if hasattr(mesh, "release_device_records"):
+            mesh.release_device_records()  # the half-edge streams replace them
         nnz, nhe, ntiles, ms = c_int64(), c_int64(), c_int32(), c_float()
         eng._ck(eng.lib.fvm_mesh_info(h, byref(nnz), byref(nhe), byref(ntiles), byref(ms)))
         self.nnz, self.n_halfedges, self.n_tiles, self.build_ms = (
@@ -405,6 +436,22 @@ class DeviceMesh:
                 self.eng.lib.fvm_mesh_debug_copy(self.handle, which, _ptr(arr), arr.nbytes)
             )
         return tiles, meta, ce
+
+    def control_volumes(self):
+        """Host copy of the device control volumes (owned rows are meaningful)."""
+        cv = numpy.empty(self.n, dtype=numpy.float64)
+        self.eng._ck(self.eng.lib.fvm_mesh_debug_copy(self.handle, 3, _ptr(cv), cv.nbytes))
+        return cv
+
+    def boundary_vertices_tri(self):
+        """Triangle meshes: boundary flags of the owned vertices, derived on the
+        device from the pattern (edges that belong to exactly one cell)."""
+        out = self.eng.alloc(self.n)
+        self.eng._ck(self.eng.lib.fvm_dev_memset(self.eng.ctx, out.ptr, 0, self.n))
+        self.eng._ck(self.eng.lib.fvm_mesh_boundary_tri(self.handle, out.ptr))
+        flags = numpy.empty(self.n, dtype=numpy.uint8)
+        out.download(flags)
+        return flags.astype(bool)
 
     def pattern(self):
         """Host copy of ``(indptr, indices)`` (int32), fetched once."""

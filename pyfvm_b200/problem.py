@@ -11,7 +11,7 @@ import numpy
 from scipy import sparse
 
 from . import codegen, lowering
-from .engine import Engine, device_mesh, _mesh_arrays
+from .engine import Engine, device_mesh, _mesh_arrays, _cell_dim
 
 _KEEP_BIT = 0x80  # record is covered by at least one edge term without subdomain
 
@@ -21,6 +21,10 @@ def _edge_bits(mesh, lowered):
     bits, rec_mask, nbit = [], None, 0
     if all(t.subdomain is None for t in lowered.edge):
         return [None] * len(lowered.edge), None
+    if hasattr(mesh, "device_records"):
+        raise NotImplementedError(
+            "dS terms restricted to a subdomain need the cells on the host; use a host mesh"
+        )
     idx = numpy.asarray(mesh.idx_hierarchy)
     shape = idx.shape[1:]
     rec_mask = numpy.zeros(shape, dtype=numpy.uint8)
@@ -73,7 +77,7 @@ class _DeviceProblem:
 
     def __init__(self, obj, mesh, kind, device=None, fmad=False, row_range=None):
         self.eng = eng = Engine.get(device)
-        _, coords, dim = _mesh_arrays(mesh)
+        coords, dim = _mesh_arrays(mesh)
         self.n = n = coords.shape[0]
         lower = lowering.lower_linear if kind == "linear" else lowering.lower_nonlinear
         self.lowered = lowered = lower(obj, dim)
@@ -85,8 +89,7 @@ class _DeviceProblem:
             if kind == "linear"
             else [codegen.MODE_RESIDUAL, codegen.MODE_JACOBIAN]
         )
-        cell_dim = numpy.asarray(mesh.idx_hierarchy).ndim - 1  # (2,3,c): 2, (2,3,4,c): 3
-        tune = codegen.tuning(cell_dim)
+        tune = codegen.tuning(_cell_dim(mesh))
         self.functors = {m: codegen.generate(lowered, m, ebits, vbits, tune) for m in modes}
         need_el = any(f.uses_el for f in self.functors.values())
         # row_range = (first owned vertex, owned rows): row-partitioned multi-GPU runs
