@@ -272,8 +272,10 @@ class PeerHalo:
             "flag_off": self.flag_off,
             "recv": part.recv,  # owner -> (first ghost slot, count) in MY local numbering
         }
-        infos = [None] * part.world
-        dist.all_gather_object(infos, mine, group=group)
+        infos = [mine]
+        if part.world > 1:
+            infos = [None] * part.world
+            dist.all_gather_object(infos, mine, group=group)
         self.peer = {}
         for p in part.neighbours:
             base = c_void_p()
@@ -296,7 +298,8 @@ class PeerHalo:
         self.n_flags = len(flags)
         self.timeout_ptr = self.buf.ptr + self.flag_off + 8 * part.world
         self.epoch = 0
-        dist.barrier(group=group)  # every mapping exists before the first push
+        if part.world > 1:
+            dist.barrier(group=group)  # every mapping exists before the first push
 
     def u_ptr(self, k):
         return self.buf.ptr + k * self.ustride
