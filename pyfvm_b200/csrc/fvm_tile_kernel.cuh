@@ -413,8 +413,8 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
 #if FVM_EDGE_FACTORED
           // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
 #if FVM_DIM == 3
-          // tetrahedra: ~10 half-edges per slot; read them two at a time, the first
-          // pair with one 16-byte load where it is 16-byte aligned
+          // tetrahedra: ~10 half-edges per slot; after an odd head element the slot's
+          // half-edges are read two at a time with 16-byte loads
           double ce;
           int k = lo;
           if (((lo ^ ce_odd) & 1) == 0 && hi - lo > 1) {
@@ -426,9 +426,11 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const 
             k = lo + 1;
           }
 #pragma unroll 1
-          for (; k + 1 < hi; k += 2) {  // k keeps the parity of an aligned pair or of lo + 1
-            ce += s_ce[k];
-            ce += s_ce[k + 1];
+          for (; k + 1 < hi; k += 2) {  // k is 16-byte aligned from here on
+            // 16-byte loads: lanes a stride of ~10 half-edges apart hit distinct banks
+            const double2 p = *(const double2*)(s_ce + k);
+            ce += p.x;  // still in half-edge order
+            ce += p.y;
           }
           if (k < hi) ce += s_ce[k];
 #else
