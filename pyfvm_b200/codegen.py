@@ -31,6 +31,8 @@ def tuning(cell_dim=2):
         "ctas_per_sm": int(os.environ.get("FVM_CTAS_PER_SM", "0")),
         # fold the ce_ratios of a slot first and evaluate ce*g(slot) once
         "factor_ce": int(os.environ.get("FVM_FACTOR_CE", "1")),
+        # resident CTAs per SM the register allocation must allow (__launch_bounds__)
+        "min_ctas": int(os.environ.get("FVM_MIN_CTAS", "0")),
     }
 
 # functor outputs per mode: (edge D, O, C), (vertex L, C), (dirichlet coeff, val)
@@ -189,6 +191,7 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         "FVM_CONSUMER_WARPS": tune["consumer_warps"],
         "FVM_STAGES": tune["stages"],
         "FVM_EDGE_FACTORED": int(factored),
+        "FVM_MIN_CTAS": tune["min_ctas"],
         "FVM_EDGE_USES_X": int(edge_x),
         "FVM_EDGE_USES_U": int(edge_u),
         "FVM_VERT_USES_X": int(vert_x),

@@ -273,7 +273,14 @@ __device__ __forceinline__ FvmTileDesc fvm_load_desc(const FvmTileDesc* g) {
   return d;
 }
 
-extern "C" __global__ void __launch_bounds__(FVM_THREADS) fvm_tile_kernel(const FvmTileArgs a) {
+// FVM_MIN_CTAS > 0 makes the register allocation fit that many CTAs per SM; measured
+// on C4: unset (72 registers, 5 CTAs/SM) beats both 6 CTAs (64) and 4 CTAs (85)
+#if defined(FVM_MIN_CTAS) && FVM_MIN_CTAS > 0
+extern "C" __global__ void __launch_bounds__(FVM_THREADS, FVM_MIN_CTAS)
+#else
+extern "C" __global__ void __launch_bounds__(FVM_THREADS)
+#endif
+    fvm_tile_kernel(const FvmTileArgs a) {
   extern __shared__ __align__(16) unsigned char sm[];
   const FvmSmemLayout L = a.L;  // computed by the host (fvm_smem_layout)
   unsigned long long* full = (unsigned long long*)(sm + L.bar);
