@@ -1,0 +1,140 @@
+"""GPU tier: edge cases of the path -- vertices in no cell, terms that leave
+records out of the pattern, int32 index input, very high vertex degree, FMA
+build, geometry re-upload."""
+import numpy
+import pytest
+import sympy
+
+from . import parity, problems
+
+pytestmark = pytest.mark.gpu
+
+
+def _both():
+    import oracle
+    import pyfvm_b200
+
+    return oracle, pyfvm_b200
+
+
+def _compare_linear(prob_factory, mesh, **kw):
+    oracle, eng = _both()
+    s = {}
+    A_ref, b_ref = oracle.discretize_linear(prob_factory(oracle.form_language), mesh, scales=s)
+    A, b = eng.discretize_linear(prob_factory(eng.form_language), mesh, **kw)
+    parity.assert_matrix_close(A, A_ref, s["matrix"])
+    parity.assert_vector_close(b, b_ref, s["rhs"])
+    return A, b
+
+
+def reaction_only_left(fl):
+    """The only dS term is restricted to a subdomain: records of the other cells
+    leave the sparsity pattern (as the reference's masked COO blocks do)."""
+    left = problems.LeftHalf()
+
+    class P:
+        def apply(self, u):
+            return (
+                fl.integrate(lambda x: -fl.n_dot_grad(u(x)), fl.dS, subdomains=[left])
+                + fl.integrate(lambda x: u(x), fl.dV)
+                - fl.integrate(lambda x: 1.0 + x[0], fl.dV)
+            )
+
+        def dirichlet(self, u):
+            return []
+
+    return P()
+
+
+def test_isolated_vertices_keep_their_diagonal():
+    from pyfvm_b200 import meshes
+
+    p, c = problems.rectangle(9, 7)
+    extra = numpy.array([[5.0, 5.0], [6.0, 5.0], [7.0, 5.5]])
+    mesh = meshes.Mesh(numpy.concatenate([p[:10], extra[:1], p[10:], extra[1:]]), c + (c >= 10))
+    assert (mesh.control_volumes == 0.0).sum() == 3
+    A, b = _compare_linear(problems.poisson, mesh)
+    assert A.nnz == A.shape[0] + 2 * (8 * 7 + 9 * 6 + 8 * 6)  # diagonal kept for every vertex
+    _compare_linear(problems.reaction_x, mesh)
+
+
+def test_restricted_edge_term_shrinks_the_pattern():
+    from pyfvm_b200 import meshes
+
+    mesh = meshes.Mesh(*meshes.jitter(*problems.rectangle(33, 17), scale=0.15, seed=2))
+    A, _ = _compare_linear(reaction_only_left, mesh)
+    full, _ = _compare_linear(problems.poisson, mesh)
+    assert A.nnz < full.nnz
+
+
+def test_int32_index_input():
+    from pyfvm_b200 import meshes
+
+    mesh = meshes.Mesh(*problems.rectangle(21, 13))
+    mesh._idx = numpy.ascontiguousarray(mesh.idx_hierarchy.astype(numpy.int32))
+    _compare_linear(problems.convection_diffusion, mesh)
+
+
+def _fan(k):
+    """k triangles around a central vertex: a row with 2k half-edges."""
+    ang = numpy.linspace(0.0, 2.0 * numpy.pi, k, endpoint=False)
+    pts = numpy.concatenate([[[0.0, 0.0]], numpy.stack([numpy.cos(ang), numpy.sin(ang)], 1)])
+    ring = numpy.arange(1, k + 1)
+    cells = numpy.stack([numpy.zeros(k, dtype=numpy.int64), ring, numpy.roll(ring, -1)], 1)
+    return pts, cells
+
+
+def test_high_degree_vertex():
+    from pyfvm_b200 import engine, meshes
+
+    mesh = meshes.Mesh(*_fan(1000))  # centre row: 2000 half-edges, 1001 slots
+    _compare_linear(problems.poisson, mesh)
+    _compare_linear(problems.reaction_x, mesh)
+    too_big = meshes.Mesh(*_fan(1100))
+    with pytest.raises(engine.FvmError, match="2047"):
+        _both()[1].discretize_linear(problems.poisson(_both()[1].form_language), too_big)
+
+
+def test_fma_build_stays_within_tolerance():
+    from pyfvm_b200 import meshes
+
+    mesh = meshes.Mesh(*meshes.jitter(*problems.cube(9), scale=0.2, seed=3))
+    _compare_linear(problems.reaction_x, mesh, fmad=True)
+
+
+def test_geometry_reupload_matches_fresh_mesh():
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import meshes, problem
+
+    p, c = problems.rectangle(25, 14)
+    mesh = meshes.Mesh(p, c)
+    lp = problem.LinearProblem(problems.convection_diffusion(eng.form_language), mesh)
+    A0, b0 = lp.assemble()
+    p2, _ = meshes.jitter(p, c, scale=0.1, seed=4)
+    moved = meshes.Mesh(p2, c)
+    lp.update_geometry(
+        ce=numpy.asarray(moved.ce_ratios).reshape(-1), coords=p2, cv=moved.control_volumes
+    )
+    A1, b1 = lp.assemble()
+    A2, b2 = eng.discretize_linear(problems.convection_diffusion(eng.form_language), moved)
+    assert A1.indices.tobytes() == A2.indices.tobytes()
+    assert A1.data.tobytes() == A2.data.tobytes() and b1.tobytes() == b2.tobytes()
+    assert A1.data.tobytes() != A0.data.tobytes()
+
+
+def test_newton_on_device_generated_mesh():
+    """pyfvm.newton [README:113-121] unchanged on top of a device-generated mesh."""
+    import pyfvm
+    from pyfvm_b200 import device_meshes as dm
+    from scipy.sparse import linalg
+
+    d = dm.device_rectangle_tri(numpy.linspace(0.0, 2.0, 101), numpy.linspace(0.0, 1.0, 51))
+    import pyfvm_b200 as eng
+
+    f, jacobian = pyfvm.discretize(problems.bratu(eng.form_language), d)
+
+    def jacobian_solver(u0, rhs):
+        return linalg.spsolve(jacobian.get_linear_operator(u0), rhs)
+
+    u = pyfvm.newton(f.eval, jacobian_solver, numpy.zeros(len(d.points)), verbose=False)
+    assert u.max() == pytest.approx(0.28395, abs=1e-5)
