@@ -16,12 +16,16 @@
 // global load.  Ranges start at even vertices and have even length: every bulk
 // copy is 16-byte aligned for 8-byte elements.
 //
-// slot_meta packs, per CSR slot, everything the slot-parallel pass needs:
+// slot_meta has one entry per OFF-DIAGONAL CSR slot (the diagonal slot of a row owns
+// no half-edge; the row pass writes it), packing everything the slot-parallel pass
+// needs:
 //   bits  0..11  first half-edge of the slot, relative to the tile   (< 4096)
 //   bits 12..19  row of the slot, relative to the tile               (< 256)
-//   bits 20..31  index of the slot's column in the tile's vertex table
+//   bit  20      the slot sits after its row's diagonal slot
+//   bits 21..31  index of the slot's column in the tile's vertex table
 //                (FVM_XLOC_NONE: not covered -> cold global gather)
-// The pattern build sizes the tiles so that these ranges always hold.
+// Entry k of a tile (k counted from the tile's first off-diagonal slot) is CSR slot
+// s0 + k + row + after.  The pattern build sizes the tiles so that the ranges hold.
 #define FVM_NHALO 8
 struct FvmTileDesc {  // 128 bytes, one per tile
   long long h0;
@@ -39,10 +43,12 @@ struct FvmTileDesc {  // 128 bytes, one per tile
 #define FVM_META_ROW_BITS 8
 #define FVM_META_LO_MASK 0xfffu
 #define FVM_META_ROW_MASK 0xffu
-#define FVM_XLOC_NONE 0xfffu  // slot_meta column field: column not in the tile's table
+#define FVM_META_AFTER_BIT 20
+#define FVM_META_XL_SHIFT 21
+#define FVM_XLOC_NONE 0x7ffu  // slot_meta column field: column not in the tile's table
 #define FVM_TILE_MAX_HE 4095    // half-edges per tile
 #define FVM_TILE_MAX_ROWS 255   // rows per tile
-#define FVM_TILE_MAX_XTAB 4094  // vertex-table entries per tile
+#define FVM_TILE_MAX_XTAB 2046  // vertex-table entries per tile
 
 // Dynamic shared-memory carve-up of one CTA, identical on host and device:
 //   [full/empty mbarriers][stage 0][stage 1]...
@@ -61,7 +67,7 @@ struct FvmTileArgs {
   const FvmTileDesc* tiles;        // [ntiles]
   const int* indptr;               // [nrows+1] CSR row pointer
   const int* colidx;               // [nnz] column (local vertex id) of every slot
-  const unsigned* slot_meta;       // [nnz] packed first half-edge | row | column location
+  const unsigned* slot_meta;       // [nnz - nrows] packed half-edge | row | after | column
   const unsigned short* row_diag;  // [nrows] offset of the diagonal slot inside its row
   const double* he_ce;             // [H] edge_ce_ratio in half-edge order
   const double* he_el;             // [H] edge_length in half-edge order (or null)

@@ -26,7 +26,7 @@
 //                    halo ranges holding the neighbour columns) of coordinates
 //                    and u -- one or more tiles ahead of the math;
 //   consumer warps : sweep the tile twice.
-//                    Pass A is SLOT-parallel: the tile's CSR slots are cut into
+//                    Pass A is SLOT-parallel: the tile's off-diagonal CSR slots are cut into
 //                    32-slot chunks dealt round-robin to the warps; lane l takes
 //                    slot c+l, folds the slot's ce_ratios in half-edge order out of
 //                    shared memory (consecutive lanes read consecutive addresses),
@@ -145,7 +145,7 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
   *(FvmTileDesc*)(stage + L.desc) = d;
   unsigned total = 0;
   const FvmStage g_ce = fvm_stage(a.he_ce + d.h0, (unsigned)d.nhe * 8u);
-  const FvmStage g_meta = fvm_stage(a.slot_meta + d.s0, (unsigned)d.nsl * 4u);
+  const FvmStage g_meta = fvm_stage(a.slot_meta + (d.s0 - d.r0), (unsigned)(d.nsl - d.nr) * 4u);
   const FvmStage g_rp = fvm_stage(a.indptr + d.r0, (unsigned)(d.nr + 1) * 4u);
   total += g_ce.bytes + g_meta.bytes + g_rp.bytes;
   // vertex table: own rows, then the halo ranges (even starts, even counts)
@@ -334,7 +334,9 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
 
     const double* s_ce = (const double*)(stage + L.ce + fvm_shift(a.he_ce + sd->h0));
     const int ce_odd = (int)(fvm_shift(a.he_ce + sd->h0) >> 3);  // 1: s_ce[0] sits at 8 mod 16
-    const unsigned* s_meta = (const unsigned*)(stage + L.meta + fvm_shift(a.slot_meta + d_s0));
+    const int d_nk = d_nsl - d_nr;  // off-diagonal slots of the tile
+    const unsigned* s_meta =
+        (const unsigned*)(stage + L.meta + fvm_shift(a.slot_meta + (d_s0 - d_r0)));
     const int xoff = v0 - sd->own_start;  // table index of the tile's first row
     const int* s_rp = (const int*)(stage + L.rowptr + fvm_shift(a.indptr + d_r0));
 #if FVM_EDGE_USES_EL
@@ -370,116 +372,118 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
 #endif
 
     {
-      // ---------------- pass A: one lane per CSR slot -------------------------
+      // ---------------- pass A: one lane per off-diagonal CSR slot -------------
       // 32-slot chunks dealt round-robin to the math warps
 #pragma unroll 1
-      for (int s = cw * 32 + lane; s < d_nsl; s += FVM_NCT) {
-        const unsigned meta = s_meta[s];
+      for (int k = cw * 32 + lane; k < d_nk; k += FVM_NCT) {
+        const unsigned meta = s_meta[k];
         const int lo = (int)(meta & FVM_META_LO_MASK);
-        const int hi = (s + 1 < d_nsl) ? (int)(s_meta[s + 1] & FVM_META_LO_MASK) : d_nhe;
+        const int hi = (k + 1 < d_nk) ? (int)(s_meta[k + 1] & FVM_META_LO_MASK) : d_nhe;
+        const int g = (int)((meta >> FVM_META_LO_BITS) & FVM_META_ROW_MASK);  // row of the slot
+        // CSR slot (tile-relative): one diagonal slot per earlier row, plus this row's
+        const int s = k + g + (int)((meta >> FVM_META_AFTER_BIT) & 1u);
         double aD = 0.0, aO = 0.0, aC = 0.0;
-        if (lo < hi) {  // the diagonal slot owns no half-edge; pass B writes it
-          const int g = (int)((meta >> FVM_META_LO_BITS) & FVM_META_ROW_MASK);  // row of the slot
-          double x00 = 0.0, x01 = 0.0, x02 = 0.0, u0 = 0.0;
-          double x10 = 0.0, x11 = 0.0, x12 = 0.0, u1 = 0.0;
+        double x00 = 0.0, x01 = 0.0, x02 = 0.0, u0 = 0.0;
+        double x10 = 0.0, x11 = 0.0, x12 = 0.0, u1 = 0.0;
 #if FVM_EDGE_USES_X
-          {
-            const double2 q0 = *(const double2*)(s_xy + FVM_XS * (xoff + g));
-            x00 = q0.x;
-            x01 = q0.y;
+        {
+          const double2 q0 = *(const double2*)(s_xy + FVM_XS * (xoff + g));
+          x00 = q0.x;
+          x01 = q0.y;
 #if FVM_DIM == 3
-            x02 = s_xy[FVM_XS * (xoff + g) + 2];
-#endif
-          }
-#endif
-#if FVM_EDGE_USES_U
-          u0 = s_u[xoff + g];
-#endif
-#if FVM_EDGE_USES_X || FVM_EDGE_USES_U
-          const unsigned xl = meta >> (FVM_META_LO_BITS + FVM_META_ROW_BITS);
-          if (xl != FVM_XLOC_NONE) {
-#if FVM_EDGE_USES_X
-            const double2 q = *(const double2*)(s_xy + FVM_XS * xl);
-            x10 = q.x;
-            x11 = q.y;
-#if FVM_DIM == 3
-            x12 = s_xy[FVM_XS * xl + 2];
-#endif
-#endif
-#if FVM_EDGE_USES_U
-            u1 = s_u[xl];
-#endif
-          } else {  // column outside the staged halo ranges: gather it (cold path)
-            const double4 gq = fvm_gather_column(a.colidx, a.coords, a.u, d_s0 + s);
-            x10 = gq.x;
-            x11 = gq.y;
-            x12 = gq.z;
-            u1 = gq.w;
-          }
-#endif
-#if FVM_EDGE_FACTORED
-          // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
-#if FVM_DIM == 3
-          // tetrahedra: ~10 half-edges per slot; after an odd head element the slot's
-          // half-edges are read two at a time with 16-byte loads
-          double ce;
-          int k = lo;
-          if (((lo ^ ce_odd) & 1) == 0 && hi - lo > 1) {
-            const double2 p = *(const double2*)(s_ce + lo);
-            ce = p.x + p.y;
-            k = lo + 2;
-          } else {
-            ce = s_ce[lo];
-            k = lo + 1;
-          }
-#pragma unroll 1
-          for (; k + 1 < hi; k += 2) {  // k is 16-byte aligned from here on
-            // 16-byte loads: lanes a stride of ~10 half-edges apart hit distinct banks
-            const double2 p = *(const double2*)(s_ce + k);
-            ce += p.x;  // still in half-edge order
-            ce += p.y;
-          }
-          if (k < hi) ce += s_ce[k];
-#else
-          // triangles: two half-edges per interior slot
-          double ce = s_ce[lo];
-          if (hi - lo > 1) {
-            ce += s_ce[lo + 1];
-            if (hi - lo > 2) {
-#pragma unroll 1
-              for (int k = lo + 2; k < hi; ++k) ce += s_ce[k];
-            }
-          }
-#endif
-          fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, 0.0, 0xffu, aD, aO, aC);
-#else
-#pragma unroll 1
-          for (int k = lo; k < hi; ++k) {
-            const double ce = s_ce[k];
-            double el = 0.0;
-            unsigned m = 0xffu;
-#if FVM_EDGE_USES_EL
-            el = s_el[k];
-#endif
-#if FVM_EDGE_MASKED
-            m = s_mask[k];
-#endif
-            double D = 0.0, O = 0.0, C = 0.0;
-            fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, el, m, D, O, C);
-            aD += D;
-            aO += O;
-            aC += C;
-          }
-#endif
-#if FVM_MODE != FVM_MODE_RESIDUAL
-          a.data[d_s0 + s] = aO;  // consecutive lanes, consecutive slots: coalesced
+          x02 = s_xy[FVM_XS * (xoff + g) + 2];
 #endif
         }
+#endif
+#if FVM_EDGE_USES_U
+        u0 = s_u[xoff + g];
+#endif
+#if FVM_EDGE_USES_X || FVM_EDGE_USES_U
+        const unsigned xl = meta >> FVM_META_XL_SHIFT;
+        if (xl != FVM_XLOC_NONE) {
+#if FVM_EDGE_USES_X
+          const double2 q = *(const double2*)(s_xy + FVM_XS * xl);
+          x10 = q.x;
+          x11 = q.y;
+#if FVM_DIM == 3
+          x12 = s_xy[FVM_XS * xl + 2];
+#endif
+#endif
+#if FVM_EDGE_USES_U
+          u1 = s_u[xl];
+#endif
+        } else {  // column outside the staged halo ranges: gather it (cold path)
+          const double4 gq = fvm_gather_column(a.colidx, a.coords, a.u, d_s0 + s);
+          x10 = gq.x;
+          x11 = gq.y;
+          x12 = gq.z;
+          u1 = gq.w;
+        }
+#endif
+#if FVM_EDGE_FACTORED
+        // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
+#if FVM_DIM == 3
+        // tetrahedra: ~10 half-edges per slot; after an odd head element the slot's
+        // half-edges are read two at a time with 16-byte loads
+        double ce;
+        int kk = lo;
+        if (((lo ^ ce_odd) & 1) == 0 && hi - lo > 1) {
+          const double2 p = *(const double2*)(s_ce + lo);
+          ce = p.x + p.y;
+          kk = lo + 2;
+        } else {
+          ce = s_ce[lo];
+          kk = lo + 1;
+        }
+#pragma unroll 1
+        for (; kk + 1 < hi; kk += 2) {  // kk is 16-byte aligned from here on
+          // 16-byte loads: lanes a stride of ~10 half-edges apart hit distinct banks
+          const double2 p = *(const double2*)(s_ce + kk);
+          ce += p.x;  // still in half-edge order
+          ce += p.y;
+        }
+        if (kk < hi) ce += s_ce[kk];
+#else
+        // triangles: two half-edges per interior slot
+        double ce = s_ce[lo];
+        if (hi - lo > 1) {
+          ce += s_ce[lo + 1];
+          if (hi - lo > 2) {
+#pragma unroll 1
+            for (int kk = lo + 2; kk < hi; ++kk) ce += s_ce[kk];
+          }
+        }
+#endif
+        fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, 0.0, 0xffu, aD, aO, aC);
+#else
+        // the edge functor is evaluated per half-edge (edge_length / subdomain bits
+        // vary inside a slot)
+#pragma unroll 1
+        for (int kk = lo; kk < hi; ++kk) {
+          const double ce = s_ce[kk];
+          double el = 0.0;
+          unsigned m = 0xffu;
+#if FVM_EDGE_USES_EL
+          el = s_el[kk];
+#endif
+#if FVM_EDGE_MASKED
+          m = s_mask[kk];
+#endif
+          double D = 0.0, O = 0.0, C = 0.0;
+          fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, el, m, D, O, C);
+          aD += D;
+          aO += O;
+          aC += C;
+        }
+#endif
+#if FVM_MODE != FVM_MODE_RESIDUAL
+        a.data[d_s0 + s] = aO;  // consecutive lanes, (nearly) consecutive slots: coalesced
+#endif
 #if FVM_ACC_D
-        s_accd[s] = aD;
+        s_accd[k] = aD;
 #endif
 #if FVM_ACC_C
-        s_accc[s] = aC;
+        s_accc[k] = aC;
 #endif
       }
       // the parked shares (and pass A's CSR stores) are visible to all math warps
@@ -487,15 +491,15 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
 
       // ---------------- pass B: one lane per matrix row ------------------------
       for (int g = ra + lane; g < rb; g += 32) {
-        const int b = s_rp[g] - d_s0, e = s_rp[g + 1] - d_s0;
+        const int b = s_rp[g] - d_s0, e = s_rp[g + 1] - d_s0;  // CSR slots of the row
         double sD = 0.0, sC = 0.0;
 #pragma unroll 1
-        for (int s = b; s < e; ++s) {  // in slot order (deterministic)
+        for (int k = b - g; k < e - g - 1; ++k) {  // its off-diagonal slots, in slot order
 #if FVM_ACC_D
-          sD += s_accd[s];
+          sD += s_accd[k];
 #endif
 #if FVM_ACC_C
-          sC += s_accc[s];
+          sC += s_accc[k];
 #endif
         }
         double x00 = 0.0, x01 = 0.0, x02 = 0.0, u0 = 0.0, cvv = 0.0;

@@ -429,7 +429,7 @@ class DeviceMesh:
         """Host copies of the device layout (tests / inspection): tile descriptors,
         packed slot metadata, ce_ratios in half-edge order."""
         tiles = numpy.empty(self.n_tiles, dtype=self.TILE_DTYPE)
-        meta = numpy.empty(self.nnz, dtype=numpy.uint32)
+        meta = numpy.empty(self.nnz - self.n_rows, dtype=numpy.uint32)
         ce = numpy.empty(self.n_halfedges, dtype=numpy.float64)
         for which, arr in ((0, tiles), (1, meta), (2, ce)):
             self.eng._ck(
