@@ -113,7 +113,8 @@ typedef struct fvm_mesh_desc {
   const double* control_volumes; /* [n_vertices]; NULL: derived on the device for the
                                owned rows (needs edge_len), as sum |e|^2 ce / (2 cell_dim) */
   int32_t tile_quantum; /* 0 = default; half-edges+slots per tile              */
-  int32_t cell_dim;     /* 2 triangles, 3 tetrahedra (used when control_volumes == NULL) */
+  int32_t cell_dim;     /* 2 triangles, 3 tetrahedra (default tile size; scale of the
+                           control volumes derived when control_volumes == NULL)       */
 } fvm_mesh_desc;
 
 int fvm_mesh_create(fvm_ctx* ctx, const fvm_mesh_desc* desc, fvm_mesh** out);

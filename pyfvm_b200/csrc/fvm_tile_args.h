@@ -113,6 +113,8 @@ FVM_HD inline unsigned fvm_round16(unsigned x) { return (x + 15u) & ~15u; }
 
 FVM_HD inline unsigned fvm_coord_stride(int dim) { return dim == 2 ? 2u : 4u; }
 
+// max_slots: off-diagonal slots of the largest tile (slot_meta and the parked shares
+// have one entry per off-diagonal slot)
 FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_rows, int max_xtab,
                                             int dim, unsigned flags, int mode, int stages) {
   FvmSmemLayout L;
