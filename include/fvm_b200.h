@@ -38,6 +38,7 @@ typedef struct fvm_kernel fvm_kernel;
 #define FVM_LINEAR 0   /* discretize_linear: CSR values + rhs   [README.md:49]  */
 #define FVM_RESIDUAL 1 /* f.eval(u)                             [README.md:121] */
 #define FVM_JACOBIAN 2 /* jacobian.get_linear_operator(u0)      [README.md:116] */
+#define FVM_SPMV 3     /* y = A x on the mesh's pattern (fvm_spmv)               */
 
 /* fvm_kernel_create flags: what the functor set reads (must equal the
  * FVM_FLAGS the generated prelude defines) */
@@ -195,6 +196,22 @@ int fvm_kernel_source(const char* functor_src, char* out, size_t out_len, size_t
 int fvm_assemble(fvm_mesh* mesh, fvm_kernel* k, const uint8_t* vmask_dev,
                  const uint8_t* dirid_dev, const double* u_dev, double* data_dev,
                  double* vec_dev);
+
+/* ---- the step after the path: y = A x on the assembled system, so
+ * that a jacobian_solver callback [README.md:113-117] can run a Krylov method without
+ * leaving HBM.  Same tiles, same staged vertex tables as the assembly (no global
+ * gather of x), deterministic.  values_dev: CSR values in the mesh's pattern order
+ * (what fvm_assemble wrote); x_dev[n_vertices], y_dev[n_rows]. */
+int fvm_spmv_kernel_create(fvm_ctx* ctx, fvm_kernel** out);
+int fvm_spmv(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* values_dev, const double* x_dev,
+             double* y_dev);
+/* diag_dev[r] = A[r, r] (Jacobi preconditioner) */
+int fvm_csr_diagonal(fvm_mesh* mesh, const double* values_dev, double* diag_dev);
+/* deterministic dot product (fixed-shape two-stage reduction), z = a x + b y, z = x / d */
+int fvm_dot(fvm_ctx* ctx, const double* x_dev, const double* y_dev, int64_t n, double* out);
+int fvm_axpby(fvm_ctx* ctx, double a, const double* x_dev, double b, const double* y_dev,
+              double* z_dev, int64_t n);
+int fvm_vdiv(fvm_ctx* ctx, const double* x_dev, const double* d_dev, double* z_dev, int64_t n);
 
 /* ---- small device helpers used around the path --------------------------------*/
 /* deterministic ||x||_2 (fixed-shape two-stage reduction) [README.md:121 newton] */

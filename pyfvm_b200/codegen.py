@@ -33,6 +33,7 @@ def tuning(cell_dim=2):
         "factor_ce": int(os.environ.get("FVM_FACTOR_CE", "1")),
         # resident CTAs per SM the register allocation must allow (__launch_bounds__)
         "min_ctas": int(os.environ.get("FVM_MIN_CTAS", "0")),
+        "pair_loads": int(os.environ.get("FVM_PAIR_LOADS", "0")),
     }
 
 # functor outputs per mode: (edge D, O, C), (vertex L, C), (dirichlet coeff, val)
@@ -192,6 +193,7 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         "FVM_STAGES": tune["stages"],
         "FVM_EDGE_FACTORED": int(factored),
         "FVM_MIN_CTAS": tune["min_ctas"],
+        "FVM_PAIR_LOADS": tune["pair_loads"],
         "FVM_EDGE_USES_X": int(edge_x),
         "FVM_EDGE_USES_U": int(edge_u),
         "FVM_VERT_USES_X": int(vert_x),

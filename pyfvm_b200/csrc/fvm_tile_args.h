@@ -59,7 +59,7 @@ struct FvmSmemLayout {
   unsigned bar, stage0, stage_bytes;
   // within a stage (accd / accc: per-slot diagonal / rhs contributions waiting for
   // the row fold; dg: offset of the diagonal slot inside every row)
-  unsigned desc, ce, el, mask, meta, rowptr, cv, xy, u, dir, vmask, accd, accc, dg;
+  unsigned desc, ce, el, mask, meta, rowptr, cv, xy, u, dir, vmask, accd, accc, dg, mat;
   unsigned total;
 };
 
@@ -76,7 +76,8 @@ struct FvmTileArgs {
   const double* cv;                // [nverts] control volumes
   const unsigned char* vmask;      // [nverts] vertex-term subdomain bits (or null)
   const unsigned char* dir_id;     // [nverts] 0 = free, k = Dirichlet term k-1 wins (or null)
-  const double* u;                 // [nverts] state (residual / Jacobian modes)
+  const double* u;                 // [nverts] state (residual / Jacobian modes), x (SpMV)
+  const double* mat;               // [nnz] CSR values to multiply with (SpMV mode)
   double* data;                    // [nnz] CSR values out (assembly / Jacobian modes)
   double* vec;                     // [nrows] rhs (assembly) or F (residual) out
   int row_base;                    // local vertex id of row 0 (row partitioning)
@@ -91,6 +92,7 @@ struct FvmTileArgs {
 #define FVM_MODE_LINEAR 0    // matrix values + rhs (discretize_linear)
 #define FVM_MODE_RESIDUAL 1  // F(u) (f.eval)
 #define FVM_MODE_JACOBIAN 2  // matrix values at u (jacobian.get_linear_operator)
+#define FVM_MODE_SPMV 3      // y = A x on the mesh's pattern (Krylov solvers around the path)
 
 // What a functor set reads; decides which streams are staged in shared memory.
 #define FVM_F_EDGE_EL 1u    // edge functor reads edge_length
@@ -116,13 +118,14 @@ FVM_HD inline unsigned fvm_coord_stride(int dim) { return dim == 2 ? 2u : 4u; }
 // max_slots: off-diagonal slots of the largest tile (slot_meta and the parked shares
 // have one entry per off-diagonal slot)
 FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_rows, int max_xtab,
-                                            int dim, unsigned flags, int mode, int stages) {
+                                            int dim, unsigned flags, int mode, int stages,
+                                            int max_csr_slots) {
   FvmSmemLayout L;
   const unsigned he = (unsigned)max_he, sl = (unsigned)max_slots, nr = (unsigned)max_rows;
   unsigned o = 0;  // within a stage
   const unsigned xt = (unsigned)max_xtab;
   L.desc = o;   o += 128;
-  L.ce = o;     o += fvm_round16(he * 8u) + 16u;
+  L.ce = o;     o += (mode != FVM_MODE_SPMV) ? fvm_round16(he * 8u) + 16u : 0u;
   L.el = o;     o += (flags & FVM_F_EDGE_EL) ? fvm_round16(he * 8u) + 16u : 0u;
   L.mask = o;   o += (flags & FVM_F_EDGE_MASK) ? fvm_round16(he) + 16u : 0u;
   L.meta = o;   o += fvm_round16(sl * 4u) + 16u;
@@ -135,6 +138,7 @@ FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_r
   L.accd = o;   o += (flags & FVM_F_EDGE_D) ? fvm_round16(sl * 8u) : 0u;
   L.accc = o;   o += (flags & FVM_F_EDGE_C) ? fvm_round16(sl * 8u) : 0u;
   L.dg = o;     o += (mode != FVM_MODE_RESIDUAL) ? fvm_round16(nr * 2u) + 16u : 0u;
+  L.mat = o;    o += (mode == FVM_MODE_SPMV) ? fvm_round16((unsigned)max_csr_slots * 8u) + 16u : 0u;
   L.stage_bytes = o;
   L.bar = 0;
   L.stage0 = fvm_round16(16u * (unsigned)stages);  // 2 x 8B mbarriers per stage

@@ -4,6 +4,9 @@
 //   FVM_MODE_LINEAR   : matrix values + rhs of pyfvm.discretize_linear  [README:49]
 //   FVM_MODE_RESIDUAL : f.eval(u)                                       [README:121,136]
 //   FVM_MODE_JACOBIAN : jacobian.get_linear_operator(u0) values         [README:116]
+// plus FVM_MODE_SPMV : y = A x on the same pattern and tiles (the Krylov solver a
+// jacobian_solver callback [README:113-117] can run without leaving HBM); it uses no
+// functor: slot value times x of the slot's column, row fold as in the other modes.
 //
 // It is compiled at run time by NVRTC after a generated prelude that defines
 //   FVM_MODE, FVM_DIM, FVM_FLAGS (FVM_F_* bits), FVM_CONSUMER_WARPS, FVM_STAGES,
@@ -65,11 +68,16 @@
 #define FVM_NCT (32 * FVM_CONSUMER_WARPS)  // consumer threads
 #define FVM_THREADS (FVM_NCT + 32)         // + one producer warp
 #define FVM_FULL 0xffffffffu
+#ifndef FVM_PAIR_LOADS
+#define FVM_PAIR_LOADS 0  // 1: 16-byte half-edge loads also on triangle meshes
+#endif
 
 static_assert(!(FVM_EDGE_USES_X || FVM_VERT_USES_X) || FVM_STAGE_X, "FVM_F_X missing");
 static_assert(!(FVM_EDGE_USES_U || FVM_VERT_USES_U) || FVM_STAGE_U, "FVM_F_U missing");
 static_assert(FVM_MODE != FVM_MODE_RESIDUAL || !FVM_ACC_D, "residual mode has no D output");
 static_assert(FVM_MODE != FVM_MODE_JACOBIAN || !FVM_ACC_C, "Jacobian mode has no C output");
+static_assert(FVM_MODE != FVM_MODE_SPMV || (FVM_ACC_C && !FVM_ACC_D && FVM_STAGE_U),
+              "SpMV mode parks one share per slot and gathers x");
 static_assert(!(FVM_EDGE_FACTORED && (FVM_EDGE_USES_EL || FVM_EDGE_MASKED)),
               "ce factoring needs a slot-invariant functor");
 
@@ -144,7 +152,11 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
   const int v0 = a.row_base + d.r0;
   *(FvmTileDesc*)(stage + L.desc) = d;
   unsigned total = 0;
+#if FVM_MODE != FVM_MODE_SPMV
   const FvmStage g_ce = fvm_stage(a.he_ce + d.h0, (unsigned)d.nhe * 8u);
+#else
+  const FvmStage g_ce = fvm_stage(a.mat + d.s0, (unsigned)d.nsl * 8u);  // CSR values instead
+#endif
   const FvmStage g_meta = fvm_stage(a.slot_meta + (d.s0 - d.r0), (unsigned)(d.nsl - d.nr) * 4u);
   const FvmStage g_rp = fvm_stage(a.indptr + d.r0, (unsigned)(d.nr + 1) * 4u);
   total += g_ce.bytes + g_meta.bytes + g_rp.bytes;
@@ -184,7 +196,11 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
   total += g_vm.bytes;
 #endif
   fvm_mbar_expect_tx(full, total);  // release: the descriptor store above is visible
+#if FVM_MODE != FVM_MODE_SPMV
   if (g_ce.bytes) fvm_bulk_g2s(stage + L.ce, g_ce.src, g_ce.bytes, full);
+#else
+  if (g_ce.bytes) fvm_bulk_g2s(stage + L.mat, g_ce.src, g_ce.bytes, full);
+#endif
   if (g_meta.bytes) fvm_bulk_g2s(stage + L.meta, g_meta.src, g_meta.bytes, full);
   fvm_bulk_g2s(stage + L.rowptr, g_rp.src, g_rp.bytes, full);
 #if FVM_EDGE_USES_EL
@@ -332,8 +348,12 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
     const int ra = (d_nr * cw) / FVM_CONSUMER_WARPS;
     const int rb = (d_nr * (cw + 1)) / FVM_CONSUMER_WARPS;
 
+#if FVM_MODE != FVM_MODE_SPMV
     const double* s_ce = (const double*)(stage + L.ce + fvm_shift(a.he_ce + sd->h0));
     const int ce_odd = (int)(fvm_shift(a.he_ce + sd->h0) >> 3);  // 1: s_ce[0] sits at 8 mod 16
+#else
+    const double* s_mat = (const double*)(stage + L.mat + fvm_shift(a.mat + d_s0));
+#endif
     const int d_nk = d_nsl - d_nr;  // off-diagonal slots of the tile
     const unsigned* s_meta =
         (const unsigned*)(stage + L.meta + fvm_shift(a.slot_meta + (d_s0 - d_r0)));
@@ -377,8 +397,10 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
 #pragma unroll 1
       for (int k = cw * 32 + lane; k < d_nk; k += FVM_NCT) {
         const unsigned meta = s_meta[k];
+#if FVM_MODE != FVM_MODE_SPMV
         const int lo = (int)(meta & FVM_META_LO_MASK);
         const int hi = (k + 1 < d_nk) ? (int)(s_meta[k + 1] & FVM_META_LO_MASK) : d_nhe;
+#endif
         const int g = (int)((meta >> FVM_META_LO_BITS) & FVM_META_ROW_MASK);  // row of the slot
         // CSR slot (tile-relative): one diagonal slot per earlier row, plus this row's
         const int s = k + g + (int)((meta >> FVM_META_AFTER_BIT) & 1u);
@@ -420,9 +442,11 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
           u1 = gq.w;
         }
 #endif
-#if FVM_EDGE_FACTORED
+#if FVM_MODE == FVM_MODE_SPMV
+        aC = s_mat[s] * u1;
+#elif FVM_EDGE_FACTORED
         // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
-#if FVM_DIM == 3
+#if FVM_DIM == 3 || FVM_PAIR_LOADS
         // tetrahedra: ~10 half-edges per slot; after an odd head element the slot's
         // half-edges are read two at a time with 16-byte loads
         double ce;
@@ -476,7 +500,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
           aC += C;
         }
 #endif
-#if FVM_MODE != FVM_MODE_RESIDUAL
+#if FVM_MODE == FVM_MODE_LINEAR || FVM_MODE == FVM_MODE_JACOBIAN
         a.data[d_s0 + s] = aO;  // consecutive lanes, (nearly) consecutive slots: coalesced
 #endif
 #if FVM_ACC_D
@@ -513,11 +537,14 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
 #endif
         }
 #endif
-#if FVM_STAGE_U && (FVM_VERT_USES_U)
+#if FVM_STAGE_U && (FVM_VERT_USES_U || FVM_MODE == FVM_MODE_SPMV)
         u0 = s_u[xoff + g];
 #endif
 #if FVM_STAGE_CV
         cvv = s_cv[g];
+#endif
+#if FVM_MODE == FVM_MODE_SPMV
+        sC += s_mat[b + (int)s_dg[g]] * u0;  // the diagonal entry closes the row
 #endif
 #if FVM_HAS_VERTEX
         {
@@ -543,7 +570,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
           fvm_dirichlet(dir, u0, x00, x01, x02, dc, dv);
           sD = dc;       // row := coeff * e_row
           out_vec = dv;  // rhs := -affine (linear) / F := condition(u) (residual)
-#if FVM_MODE != FVM_MODE_RESIDUAL
+#if FVM_MODE == FVM_MODE_LINEAR || FVM_MODE == FVM_MODE_JACOBIAN
           // Dirichlet rows keep their pattern but store explicit zeros off the
           // diagonal (ordered after pass A's stores by the barrier above)
 #pragma unroll 1
@@ -551,7 +578,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
 #endif
         }
 #endif
-#if FVM_MODE != FVM_MODE_RESIDUAL
+#if FVM_MODE == FVM_MODE_LINEAR || FVM_MODE == FVM_MODE_JACOBIAN
         a.data[d_s0 + b + (int)s_dg[g]] = sD;
 #endif
 #if FVM_MODE != FVM_MODE_JACOBIAN

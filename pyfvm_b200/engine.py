@@ -112,6 +112,12 @@ SYMBOLS = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
+    "fvm_spmv_kernel_create": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "fvm_spmv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fvm_csr_diagonal": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "fvm_dot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double)]),
+    "fvm_axpby": (c_int, [c_void_p, c_double, c_void_p, c_double, c_void_p, c_void_p, c_int64]),
+    "fvm_vdiv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
     "fvm_norm2": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double)]),
     "fvm_gather_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "fvm_ipc_export": (c_int, [c_void_p, c_void_p, c_char_p]),

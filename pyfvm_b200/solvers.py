@@ -1,0 +1,174 @@
+"""The step *after* the hot path, kept in HBM: SpMV on the
+assembled system and a Jacobi-preconditioned BiCGStab, so that the
+``jacobian_solver(u0, rhs)`` callback of ``pyfvm.newton`` [README:113-121] -- a
+host ``spsolve`` in the README -- and the whole Newton loop can run without the
+matrix ever crossing PCIe.
+
+The reference leaves the solver to the user (scipy ``spsolve`` [README:51, 117],
+pyamg [README:67-77]); nothing here replaces reference code.  ``y = A x`` runs
+the assembly's own tile kernel in SpMV mode (``fvm_spmv``): same tiles, x gathered
+from the staged vertex tables, rows folded in slot order -- deterministic.
+"""
+import ctypes
+from ctypes import byref, c_double, c_void_p
+
+import numpy
+
+from . import codegen
+
+
+class DeviceSystem:
+    """``A`` = (pattern of a device mesh, CSR values in HBM) for square systems."""
+
+    def __init__(self, dmesh, values_ptr):
+        assert dmesh.n_rows == dmesh.n and dmesh.row_base == 0, "single-GPU square systems only"
+        self.dmesh, self.eng, self.values = dmesh, dmesh.eng, values_ptr
+        self.n = dmesh.n
+        eng = self.eng
+        if getattr(eng, "_spmv_kernel", None) is None:
+            h = c_void_p()
+            eng._ck(eng.lib.fvm_spmv_kernel_create(eng.ctx, byref(h)))
+            eng._spmv_kernel = h
+        self._diag = None
+        self._work = None
+
+    def matvec(self, x_ptr, y_ptr):
+        e = self.eng
+        e._ck(e.lib.fvm_spmv(self.dmesh.handle, e._spmv_kernel, self.values, x_ptr, y_ptr))
+        e.launches += 1
+
+    def diagonal(self):
+        """Device buffer with the diagonal of the current values."""
+        if self._diag is None:
+            self._diag = self.eng.alloc(8 * self.n)
+        self.eng._ck(self.eng.lib.fvm_csr_diagonal(self.dmesh.handle, self.values, self._diag.ptr))
+        return self._diag
+
+    # -- vector helpers ---------------------------------------------------------
+    def _dot(self, x, y):
+        out = c_double()
+        self.eng._ck(self.eng.lib.fvm_dot(self.eng.ctx, x, y, self.n, byref(out)))
+        return out.value
+
+    def _axpby(self, a, x, b, y, z):
+        self.eng._ck(self.eng.lib.fvm_axpby(self.eng.ctx, a, x, b, y, z, self.n))
+
+    def bicgstab(self, b_ptr, x_ptr, tol=1e-10, maxiter=None, x0_is_zero=False):
+        """Solve ``A x = b`` (device pointers), right-preconditioned with the
+        diagonal.  Stops at ``||r|| <= tol * ||b||``.  Returns (iterations,
+        relative residual); raises ``ArithmeticError`` on breakdown or no
+        convergence."""
+        e, lib, n = self.eng, self.eng.lib, self.n
+        maxiter = maxiter or 20 * int(numpy.sqrt(n)) + 200
+        if self._work is None:
+            self._work = [e.alloc(8 * n + 16) for _ in range(8)]
+        r, r0, p, v, s, t, ph, sh = (w.ptr for w in self._work)
+        d = self.diagonal().ptr
+        bnorm = e.norm2(b_ptr, n)
+        if bnorm == 0.0:
+            e._ck(lib.fvm_dev_memset(e.ctx, x_ptr, 0, 8 * n))
+            return 0, 0.0
+        if x0_is_zero:
+            e._ck(lib.fvm_dev_memset(e.ctx, x_ptr, 0, 8 * n))
+            self._axpby(1.0, b_ptr, 0.0, b_ptr, r)
+        else:
+            self.matvec(x_ptr, r)
+            self._axpby(1.0, b_ptr, -1.0, r, r)
+        self._axpby(1.0, r, 0.0, r, r0)
+        e._ck(lib.fvm_dev_memset(e.ctx, p, 0, 8 * n))
+        e._ck(lib.fvm_dev_memset(e.ctx, v, 0, 8 * n))
+        rho = alpha = omega = 1.0
+        res = e.norm2(r, n)
+        for it in range(1, maxiter + 1):
+            if res <= tol * bnorm:
+                return it - 1, res / bnorm
+            rho_new = self._dot(r0, r)
+            if rho_new == 0.0 or omega == 0.0:
+                raise ArithmeticError("BiCGStab breakdown")
+            beta = (rho_new / rho) * (alpha / omega)
+            self._axpby(1.0, p, -omega, v, p)
+            self._axpby(1.0, r, beta, p, p)
+            e._ck(lib.fvm_vdiv(e.ctx, p, d, ph, n))
+            self.matvec(ph, v)
+            r0v = self._dot(r0, v)
+            if r0v == 0.0:
+                raise ArithmeticError("BiCGStab breakdown")
+            alpha = rho_new / r0v
+            self._axpby(1.0, r, -alpha, v, s)
+            res = e.norm2(s, n)
+            if res <= tol * bnorm:
+                self._axpby(1.0, x_ptr, alpha, ph, x_ptr)
+                return it, res / bnorm
+            e._ck(lib.fvm_vdiv(e.ctx, s, d, sh, n))
+            self.matvec(sh, t)
+            tt = self._dot(t, t)
+            if tt == 0.0:
+                raise ArithmeticError("BiCGStab breakdown")
+            omega = self._dot(t, s) / tt
+            self._axpby(1.0, x_ptr, alpha, ph, x_ptr)
+            self._axpby(1.0, x_ptr, omega, sh, x_ptr)
+            self._axpby(1.0, s, -omega, t, r)
+            res = e.norm2(r, n)
+            rho = rho_new
+        if res <= tol * bnorm:
+            return maxiter, res / bnorm
+        raise ArithmeticError(f"BiCGStab did not converge: relative residual {res / bnorm:.3e}")
+
+
+def solve_linear(lp, tol=1e-10, maxiter=None):
+    """``discretize_linear`` + solve, all on the device: assemble, BiCGStab, and only
+    the solution comes back (host array)."""
+    lp.assemble_device()
+    sysm = DeviceSystem(lp.dmesh, lp.data.ptr)
+    x = lp.eng.alloc(8 * lp.n)
+    iters, relres = sysm.bicgstab(lp.vec.ptr, x.ptr, tol=tol, maxiter=maxiter, x0_is_zero=True)
+    out = numpy.empty(lp.n)
+    x.download(out)
+    return out, iters, relres
+
+
+def jacobian_solver(jacobian, tol=1e-10, maxiter=None):
+    """A ``jacobian_solver(u0, rhs) -> du`` callback for ``pyfvm.newton`` [README:113-117]
+    that refreshes the Jacobian values and solves on the device."""
+    s = jacobian._s
+    sysm = DeviceSystem(s.dmesh, s.data.ptr)
+    b, x = s.eng.alloc(8 * s.n), s.eng.alloc(8 * s.n)
+
+    def solver(u0, rhs):
+        jacobian.values_device(s.upload_u(u0))
+        b.upload(numpy.ascontiguousarray(rhs, dtype=numpy.float64))
+        sysm.bicgstab(b.ptr, x.ptr, tol=tol, maxiter=maxiter, x0_is_zero=True)
+        du = numpy.empty(s.n)
+        x.download(du)
+        return du
+
+    return solver
+
+
+def newton_device(f, jacobian, u0, tol=1e-10, max_iter=20, lin_tol=1e-10, verbose=False):
+    """``pyfvm.newton`` [README:121] with everything in HBM: residual, norm,
+    Jacobian refresh, BiCGStab and the update; one double per step crosses PCIe.
+    Same stopping rule and iteration cap as the reference's newton."""
+    s = f._s
+    e, n = s.eng, s.n
+    sysm = DeviceSystem(s.dmesh, s.data.ptr)
+    du = e.alloc(8 * n)
+    u_ptr = s.upload_u(u0)
+    steps = 0
+    while True:
+        f.eval_device(u_ptr)  # F in s.vec
+        nrm = e.norm2(s.vec.ptr, n)
+        if verbose:
+            print(f"||F(u)|| = {nrm:e}")
+        if nrm < tol:
+            break
+        if steps >= max_iter:
+            raise RuntimeError(f"Newton did not converge in {max_iter} steps (||F|| = {nrm:e})")
+        jacobian.values_device(u_ptr)
+        # J du = -F: solve for +F and subtract
+        sysm.bicgstab(s.vec.ptr, du.ptr, tol=lin_tol, x0_is_zero=True)
+        e._ck(e.lib.fvm_axpy(e.ctx, -1.0, du.ptr, u_ptr, n))
+        steps += 1
+    out = numpy.empty(n)
+    s.u.download(out)
+    return out, steps

@@ -1,0 +1,87 @@
+"""GPU tier: SpMV on the assembled system and the device Krylov / Newton built on
+it against scipy on the host."""
+import numpy
+import pytest
+from scipy.sparse import linalg
+
+from . import problems
+
+pytestmark = pytest.mark.gpu
+
+
+def _mesh(kind, *args, jit=True):
+    from pyfvm_b200 import meshes
+
+    p, c = (problems.rectangle if kind == "rect" else problems.cube)(*args)
+    if jit:
+        p, c = meshes.jitter(p, c, scale=0.2, seed=0)
+    return meshes.Mesh(p, c)
+
+
+@pytest.mark.parametrize(
+    "name,kind,args", [("convection_diffusion", "rect", (97, 61)), ("reaction_x", "cube", (12,)),
+                       ("poisson", "rect", (2, 2))]
+)
+def test_spmv_matches_scipy(name, kind, args):
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import problem, solvers
+
+    mesh = _mesh(kind, *args, jit=args != (2, 2))
+    lp = problem.LinearProblem(getattr(problems, name)(eng.form_language), mesh)
+    A, _ = lp.assemble()
+    sysm = solvers.DeviceSystem(lp.dmesh, lp.data.ptr)
+    rng = numpy.random.default_rng(0)
+    x = rng.standard_normal(lp.n)
+    xd, yd = lp.eng.to_device(x), lp.eng.alloc(8 * lp.n)
+    sysm.matvec(xd.ptr, yd.ptr)
+    y = numpy.empty(lp.n)
+    yd.download(y)
+    ref = A @ x
+    bound = 1e-13 * (abs(A) @ abs(x))
+    assert (numpy.abs(y - ref) <= bound + 1e-300).all()
+    # deterministic
+    sysm.matvec(xd.ptr, yd.ptr)
+    y2 = numpy.empty(lp.n)
+    yd.download(y2)
+    assert y.tobytes() == y2.tobytes()
+    d = numpy.empty(lp.n)
+    sysm.diagonal().download(d)
+    assert numpy.array_equal(d, A.diagonal())
+
+
+def test_device_bicgstab_solves_readme_poisson():
+    """[README:25-54] with the solve on the device instead of spsolve."""
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import meshes, problem, solvers
+
+    mesh = meshes.Mesh(*problems.rectangle(201, 101))
+    lp = problem.LinearProblem(problems.poisson(eng.form_language), mesh)
+    u, iters, relres = solvers.solve_linear(lp, tol=1e-11)
+    A, b = lp.assemble()
+    u_ref = linalg.spsolve(A, b)
+    assert relres <= 1e-11 and iters > 0
+    assert numpy.abs(u - u_ref).max() <= 1e-8 * numpy.abs(u_ref).max()
+    assert u.max() == pytest.approx(0.11387, abs=2e-5)
+
+
+def test_newton_with_device_jacobian_solver_and_device_newton():
+    """[README:86-124]: pyfvm.newton with a device jacobian_solver, and the fully
+    device-resident Newton, against the host spsolve version."""
+    import pyfvm
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import meshes, solvers
+
+    mesh = meshes.Mesh(*problems.rectangle(101, 51))
+    f, jacobian = pyfvm.discretize(problems.bratu(eng.form_language), mesh)
+    n = len(mesh.points)
+
+    def host_solver(u0, rhs):
+        return linalg.spsolve(jacobian.get_linear_operator(u0), rhs)
+
+    u_host = pyfvm.newton(f.eval, host_solver, numpy.zeros(n), verbose=False)
+    u_cb = pyfvm.newton(f.eval, solvers.jacobian_solver(jacobian), numpy.zeros(n), verbose=False)
+    u_dev, steps = solvers.newton_device(f, jacobian, numpy.zeros(n))
+    assert steps == 3
+    assert u_host.max() == pytest.approx(0.28395, abs=1e-5)
+    assert numpy.abs(u_cb - u_host).max() <= 1e-8
+    assert numpy.abs(u_dev - u_host).max() <= 1e-8
