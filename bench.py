@@ -319,6 +319,30 @@ def run_ours(args):
         rb = algorithmic_bytes(R_local, nnz, n_rows, dm.dim, True, fun.uses_el, "residual")
         res = {"ms_per_eval": rms, "algorithmic_bytes": int(rb)}
 
+    # ---- y = A x on the assembled system (the Krylov building block after the path)
+    spmv = None
+    if world == 1:
+        from pyfvm_b200 import solvers
+
+        lp.assemble_device()
+        sysm = solvers.DeviceSystem(dm, lp.data.ptr)
+        xv = eng.to_device(numpy.random.default_rng(1).standard_normal(part.n_local))
+        yv = eng.alloc(8 * n_rows)
+        for _ in range(args.warmup):
+            sysm.matvec(xv.ptr, yv.ptr)
+        eng.timer_begin()
+        for _ in range(args.steps):
+            sysm.matvec(xv.ptr, yv.ptr)
+        sms = eng.timer_end() / args.steps
+        sb = 12 * nnz + 20 * n_rows  # values + column ids, x, y, row pointers
+        spmv = {
+            "ms": sms,
+            "algorithmic_bytes": int(sb),
+            "achieved_gbs": sb / (sms * 1e-3) / 1e9,
+            "frac": sb / (sms * 1e-3) / 1e9 / peak,
+            "gflops": 2 * nnz / (sms * 1e-3) / 1e9,
+        }
+
     # ---- reduce over ranks: max time, summed work
     ms_step = ms / args.steps
     if dist is not None:
@@ -383,6 +407,7 @@ def run_ours(args):
             "frac_of_8TBs_nominal": alg / (ms_step * 1e-3) / 8e12,
         },
         "residual": res,
+        "spmv": spmv,
         "e2e_cold": cold,
         "pattern_build_ms": dm.build_ms,
         "setup_s": setup_s,
