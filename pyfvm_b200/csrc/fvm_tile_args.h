@@ -135,8 +135,9 @@ FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_r
   L.u = o;      o += (flags & FVM_F_U) ? fvm_round16(xt * 8u) : 0u;
   L.dir = o;    o += (flags & FVM_F_DIR) ? fvm_round16(nr) + 16u : 0u;
   L.vmask = o;  o += (flags & FVM_F_VMASK) ? fvm_round16(nr) + 16u : 0u;
-  L.accd = o;   o += (flags & FVM_F_EDGE_D) ? fvm_round16(sl * 8u) : 0u;
-  L.accc = o;   o += (flags & FVM_F_EDGE_C) ? fvm_round16(sl * 8u) : 0u;
+  const unsigned csl = (unsigned)max_csr_slots;  // parked shares keep the CSR row stride
+  L.accd = o;   o += (flags & FVM_F_EDGE_D) ? fvm_round16(csl * 8u) : 0u;
+  L.accc = o;   o += (flags & FVM_F_EDGE_C) ? fvm_round16(csl * 8u) : 0u;
   L.dg = o;     o += (mode != FVM_MODE_RESIDUAL) ? fvm_round16(nr * 2u) + 16u : 0u;
   L.mat = o;    o += (mode == FVM_MODE_SPMV) ? fvm_round16((unsigned)max_csr_slots * 8u) + 16u : 0u;
   L.stage_bytes = o;

@@ -162,9 +162,10 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
   total += g_ce.bytes + g_meta.bytes + g_rp.bytes;
   // vertex table: own rows, then the halo ranges (even starts, even counts)
   unsigned n_tab = (unsigned)d.own_count;
-#pragma unroll
-  for (int i = 0; i < FVM_NHALO; ++i)
-    if (i < d.nhalo) n_tab += d.hcount[i];
+  const FvmTileDesc* sd = (const FvmTileDesc*)(stage + L.desc);  // dynamic indexing: from smem
+  const int nhalo = d.nhalo;
+#pragma unroll 1
+  for (int i = 0; i < nhalo; ++i) n_tab += sd->hcount[i];
 #if FVM_EDGE_USES_EL
   const FvmStage g_el = fvm_stage(a.he_el + d.h0, (unsigned)d.nhe * 8u);
   total += g_el.bytes;
@@ -219,12 +220,11 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
     if (d.own_count)
       fvm_bulk_g2s(dst, a.coords + (size_t)d.own_start * FVM_XS, (unsigned)d.own_count * vb, full);
     dst += (unsigned)d.own_count * vb;
-#pragma unroll
-    for (int i = 0; i < FVM_NHALO; ++i) {
-      if (i < d.nhalo) {
-        fvm_bulk_g2s(dst, a.coords + (size_t)d.hstart[i] * FVM_XS, (unsigned)d.hcount[i] * vb, full);
-        dst += (unsigned)d.hcount[i] * vb;
-      }
+#pragma unroll 1
+    for (int i = 0; i < nhalo; ++i) {
+      const unsigned cnt = sd->hcount[i];
+      fvm_bulk_g2s(dst, a.coords + (size_t)sd->hstart[i] * FVM_XS, cnt * vb, full);
+      dst += cnt * vb;
     }
   }
 #endif
@@ -233,12 +233,11 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
     unsigned char* dst = stage + L.u;
     if (d.own_count) fvm_bulk_g2s(dst, a.u + d.own_start, (unsigned)d.own_count * 8u, full);
     dst += (unsigned)d.own_count * 8u;
-#pragma unroll
-    for (int i = 0; i < FVM_NHALO; ++i) {
-      if (i < d.nhalo) {
-        fvm_bulk_g2s(dst, a.u + d.hstart[i], (unsigned)d.hcount[i] * 8u, full);
-        dst += (unsigned)d.hcount[i] * 8u;
-      }
+#pragma unroll 1
+    for (int i = 0; i < nhalo; ++i) {
+      const unsigned cnt = sd->hcount[i];
+      fvm_bulk_g2s(dst, a.u + sd->hstart[i], cnt * 8u, full);
+      dst += cnt * 8u;
     }
   }
 #endif
@@ -503,11 +502,14 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
 #if FVM_MODE == FVM_MODE_LINEAR || FVM_MODE == FVM_MODE_JACOBIAN
         a.data[d_s0 + s] = aO;  // consecutive lanes, (nearly) consecutive slots: coalesced
 #endif
+        // parked at k + g: a row's shares stay contiguous and the row stride is the CSR
+        // row length (4 + 1 / 8 + 1 on the zigzag triangle grid: odd, so the row pass
+        // below reads conflict-free; the compact stride 4 / 8 would 4-way conflict)
 #if FVM_ACC_D
-        s_accd[k] = aD;
+        s_accd[k + g] = aD;
 #endif
 #if FVM_ACC_C
-        s_accc[k] = aC;
+        s_accc[k + g] = aC;
 #endif
       }
       // the parked shares (and pass A's CSR stores) are visible to all math warps
@@ -518,7 +520,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
         const int b = s_rp[g] - d_s0, e = s_rp[g + 1] - d_s0;  // CSR slots of the row
         double sD = 0.0, sC = 0.0;
 #pragma unroll 1
-        for (int k = b - g; k < e - g - 1; ++k) {  // its off-diagonal slots, in slot order
+        for (int k = b; k < e - 1; ++k) {  // its off-diagonal slots, in slot order
 #if FVM_ACC_D
           sD += s_accd[k];
 #endif
