@@ -3,6 +3,12 @@
 #ifndef FVM_TILE_ARGS_H
 #define FVM_TILE_ARGS_H
 
+// sympy.ccode prints pi as M_PI, which NVRTC does not define; this
+// header precedes the generated functors in the translation unit
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
 // A "tile" is a run of consecutive matrix rows [r0, r0+nr) whose half-edges
 // and CSR slots are contiguous in HBM:
 //   half-edges [h0, h0+nhe) -> he_ce / he_el / he_mask streams

@@ -49,10 +49,6 @@
 // warp count or the grid size, so a row-partitioned multi-GPU run is bit-identical
 // to the single-GPU run.
 
-#ifndef M_PI
-#define M_PI 3.14159265358979323846
-#endif
-
 #define FVM_EDGE_USES_EL ((FVM_FLAGS & FVM_F_EDGE_EL) != 0)
 #define FVM_EDGE_MASKED ((FVM_FLAGS & FVM_F_EDGE_MASK) != 0)
 #define FVM_STAGE_X ((FVM_FLAGS & FVM_F_X) != 0)
