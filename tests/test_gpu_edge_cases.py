@@ -138,3 +138,21 @@ def test_newton_on_device_generated_mesh():
 
     u = pyfvm.newton(f.eval, jacobian_solver, numpy.zeros(len(d.points)), verbose=False)
     assert u.max() == pytest.approx(0.28395, abs=1e-5)
+
+
+def test_piecewise_sqrt_pi_functors():
+    """Codegen gotchas end to end: Piecewise, sqrt, pi, x**4, u**3."""
+    from pyfvm_b200 import meshes
+
+    from .test_codegen_compiles import piecewise_problem
+
+    oracle, eng = _both()
+    mesh = meshes.Mesh(*meshes.jitter(*problems.rectangle(29, 17, lx=1.0), scale=0.15, seed=6))
+    f_ref, j_ref = oracle.discretize(piecewise_problem(oracle.form_language), mesh)
+    f, j = eng.discretize(piecewise_problem(eng.form_language), mesh)
+    u = 0.4 * numpy.random.default_rng(2).standard_normal(len(mesh.points))
+    s = {}
+    F_ref = f_ref.eval(u, scales=s)
+    parity.assert_vector_close(f.eval(u), F_ref, s["vec"])
+    J_ref = j_ref.get_linear_operator(u, scales=s)
+    parity.assert_matrix_close(j.get_linear_operator(u), J_ref, s["matrix"])
