@@ -138,8 +138,11 @@ __device__ __forceinline__ FvmStage fvm_stage(const void* g, unsigned nbytes) {
   return s;
 }
 
-__device__ __forceinline__ unsigned fvm_shift(const void* g) {
-  return (unsigned)((unsigned long long)g & 15ull);
+// Byte offset of element `index` (elements of `elem_bytes`) inside its 16-byte line.
+// Every base pointer of FvmTileArgs is 16-byte aligned (the host checks), so the math
+// warps derive a stream's shift from the index alone -- no 64-bit pointer arithmetic.
+__device__ __forceinline__ unsigned fvm_shift_at(long long index, unsigned elem_bytes) {
+  return ((unsigned)index * elem_bytes) & 15u;
 }
 
 __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemLayout& L,
@@ -344,24 +347,24 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
     const int rb = (d_nr * (cw + 1)) / FVM_CONSUMER_WARPS;
 
 #if FVM_MODE != FVM_MODE_SPMV
-    const double* s_ce = (const double*)(stage + L.ce + fvm_shift(a.he_ce + sd->h0));
-    const int ce_odd = (int)(fvm_shift(a.he_ce + sd->h0) >> 3);  // 1: s_ce[0] sits at 8 mod 16
+    const double* s_ce = (const double*)(stage + L.ce + fvm_shift_at(sd->h0, 8u));
+    const int ce_odd = (int)(fvm_shift_at(sd->h0, 8u) >> 3);  // 1: s_ce[0] sits at 8 mod 16
 #else
-    const double* s_mat = (const double*)(stage + L.mat + fvm_shift(a.mat + d_s0));
+    const double* s_mat = (const double*)(stage + L.mat + fvm_shift_at(d_s0, 8u));
 #endif
     const int d_nk = d_nsl - d_nr;  // off-diagonal slots of the tile
     const unsigned* s_meta =
-        (const unsigned*)(stage + L.meta + fvm_shift(a.slot_meta + (d_s0 - d_r0)));
+        (const unsigned*)(stage + L.meta + fvm_shift_at(d_s0 - d_r0, 4u));
     const int xoff = v0 - sd->own_start;  // table index of the tile's first row
-    const int* s_rp = (const int*)(stage + L.rowptr + fvm_shift(a.indptr + d_r0));
+    const int* s_rp = (const int*)(stage + L.rowptr + fvm_shift_at(d_r0, 4u));
 #if FVM_EDGE_USES_EL
-    const double* s_el = (const double*)(stage + L.el + fvm_shift(a.he_el + sd->h0));
+    const double* s_el = (const double*)(stage + L.el + fvm_shift_at(sd->h0, 8u));
 #endif
 #if FVM_EDGE_MASKED
-    const unsigned char* s_mask = stage + L.mask + fvm_shift(a.he_mask + sd->h0);
+    const unsigned char* s_mask = stage + L.mask + fvm_shift_at(sd->h0, 1u);
 #endif
 #if FVM_STAGE_CV
-    const double* s_cv = (const double*)(stage + L.cv + fvm_shift(a.cv + v0));
+    const double* s_cv = (const double*)(stage + L.cv + fvm_shift_at(v0, 8u));
 #endif
 #if FVM_STAGE_X
     const double* s_xy = (const double*)(stage + L.xy);
@@ -370,10 +373,10 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
     const double* s_u = (const double*)(stage + L.u);
 #endif
 #if FVM_HAS_DIRICHLET
-    const unsigned char* s_dir = stage + L.dir + fvm_shift(a.dir_id + v0);
+    const unsigned char* s_dir = stage + L.dir + fvm_shift_at(v0, 1u);
 #endif
 #if FVM_VERT_MASKED
-    const unsigned char* s_vm = stage + L.vmask + fvm_shift(a.vmask + v0);
+    const unsigned char* s_vm = stage + L.vmask + fvm_shift_at(v0, 1u);
 #endif
 #if FVM_ACC_D
     double* s_accd = (double*)(stage + L.accd);  // lives and dies with the stage
@@ -383,7 +386,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
 #endif
 #if FVM_MODE != FVM_MODE_RESIDUAL
     const unsigned short* s_dg =
-        (const unsigned short*)(stage + L.dg + fvm_shift(a.row_diag + d_r0));
+        (const unsigned short*)(stage + L.dg + fvm_shift_at(d_r0, 2u));
 #endif
 
     {
