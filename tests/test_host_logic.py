@@ -1,0 +1,139 @@
+"""CPU tier for the host side of the engine: the symbolic lowering
+(``pyfvm_b200.lowering``) evaluated with numpy in the kernel's half-edge semantics
+must reproduce the oracle; the form language and the code generator behave as
+the drop-in needs."""
+import numpy
+import pytest
+import sympy
+from scipy import sparse
+
+from . import problems
+
+
+def _lam(expr, args):
+    f = sympy.lambdify(args, sympy.sympify(expr), modules="numpy")
+    return lambda *a: numpy.broadcast_to(f(*a), numpy.shape(a[0])).astype(float)
+
+
+def emulate_linear(lowered, mesh):
+    """What the tile kernel computes, in numpy: every record is seen as two
+    half-edges (row, col); the row-0 expressions are evaluated with x0 = x[row],
+    x1 = x[col]; D -> (row,row), O -> (row,col), C -> -rhs[row]."""
+    from pyfvm_b200 import lowering as lo
+
+    idx = numpy.asarray(mesh.idx_hierarchy).reshape(2, -1)
+    ce = numpy.asarray(mesh.ce_ratios).reshape(-1)
+    el = numpy.sqrt(numpy.asarray(mesh.ei_dot_ei)).reshape(-1)
+    X = mesh.node_coords
+    n = len(X)
+    rows, cols, vals = [], [], []
+    rhs = numpy.zeros(n)
+    eargs = lo.X0 + lo.X1 + [lo.CE, lo.EL]
+    for t in lowered.edge:
+        keep = numpy.ones(len(ce), dtype=bool)
+        if t.subdomain is not None:
+            cm = numpy.asarray(mesh.get_cell_mask(t.subdomain))
+            keep = numpy.broadcast_to(cm, numpy.asarray(mesh.ce_ratios).shape).reshape(-1)
+        for a, b in ((idx[0], idx[1]), (idx[1], idx[0])):
+            a, b, c, l = a[keep], b[keep], ce[keep], el[keep]
+            args = [X[a, k] for k in range(3)] + [X[b, k] for k in range(3)] + [c, l]
+            rows += [a, a]
+            cols += [a, b]
+            vals += [_lam(t.outputs["diag"], eargs)(*args), _lam(t.outputs["off"], eargs)(*args)]
+            numpy.subtract.at(rhs, a, _lam(t.outputs["aff"], eargs)(*args))
+    vargs = lo.XV + [lo.CV]
+    allv = numpy.arange(n)
+    for t in lowered.vertex:
+        m = allv if t.subdomain is None else allv[mesh.get_vertex_mask(t.subdomain)]
+        args = [X[m, k] for k in range(3)] + [numpy.asarray(mesh.control_volumes)[m]]
+        rows.append(m)
+        cols.append(m)
+        vals.append(_lam(t.outputs["lin"], vargs)(*args))
+        rhs[m] -= _lam(t.outputs["aff"], vargs)(*args)
+    # every row owns its diagonal
+    rows.append(allv), cols.append(allv), vals.append(numpy.zeros(n))
+    A = sparse.coo_matrix(
+        (numpy.concatenate(vals), (numpy.concatenate(rows), numpy.concatenate(cols))), shape=(n, n)
+    ).tocsr()
+    for t in lowered.dirichlet:
+        m = allv[mesh.get_vertex_mask(t.subdomain)]
+        args = [X[m, k] for k in range(3)]
+        for i, cf, r in zip(m, _lam(t.outputs["coeff"], lo.XV)(*args), _lam(t.outputs["rhs"], lo.XV)(*args)):
+            A.data[A.indptr[i] : A.indptr[i + 1]] = 0.0
+            A[i, i] = cf
+            rhs[i] = r
+    return A, rhs
+
+
+@pytest.mark.parametrize(
+    "name,kind,args",
+    [("poisson", "rect", (9, 6)), ("convection_diffusion", "rect", (8, 7)), ("reaction_x", "rect", (7, 9)),
+     ("subdomain_problem", "rect", (11, 7)), ("reaction_x", "cube", (4,))],
+)
+def test_lowering_in_half_edge_semantics_matches_oracle(name, kind, args):
+    import oracle
+    from pyfvm_b200 import form_language, lowering, meshes
+
+    p, c = (problems.rectangle if kind == "rect" else problems.cube)(*args)
+    p, c = meshes.jitter(p, c, scale=0.15, seed=1)
+    mesh = meshes.Mesh(p, c)
+    A_ref, b_ref = oracle.discretize_linear(getattr(problems, name)(oracle.form_language), mesh)
+    low = lowering.lower_linear(getattr(problems, name)(form_language), 3)
+    A, b = emulate_linear(low, mesh)
+    assert numpy.array_equal(A.indptr, A_ref.indptr) and numpy.array_equal(A.indices, A_ref.indices)
+    scale = numpy.abs(A_ref.data).max()
+    assert numpy.abs(A.data - A_ref.data).max() <= 1e-12 * scale
+    assert numpy.abs(b - b_ref).max() <= 1e-12 * max(1.0, numpy.abs(b_ref).max())
+
+
+def test_form_language_algebra_and_exports():
+    import pyfvm.form_language as shim
+    from pyfvm_b200 import form_language as fl
+
+    for name in ("Boundary", "dS", "dV", "integrate", "n_dot_grad"):  # [README:32]
+        assert hasattr(shim, name) and hasattr(fl, name)
+    u = sympy.Function("u")
+    s = fl.integrate(lambda x: u(x), fl.dS) - 2 * fl.integrate(lambda x: 1.0, fl.dV)
+    s = -s + fl.integrate(lambda x: x[0], fl.dV, subdomains=[fl.Boundary()])
+    assert len(s.integrals) == 3
+    assert fl.Boundary().is_boundary_only and fl.Boundary().is_inside(numpy.zeros((3, 4))).all()
+
+
+def test_lowering_known_forms():
+    """App. A.2: Poisson edge block [[er, -er], [-er, er]], affine 0; Bratu derivatives."""
+    from pyfvm_b200 import form_language, lowering as lo
+
+    low = lo.lower_linear(problems.poisson(form_language), 2)
+    (e,) = low.edge
+    assert sympy.simplify(e.outputs["diag"] - lo.CE) == 0
+    assert sympy.simplify(e.outputs["off"] + lo.CE) == 0 and e.outputs["aff"] == 0
+    (v,) = low.vertex
+    assert v.outputs["lin"] == 0 and sympy.simplify(v.outputs["aff"] + lo.CV) == 0
+    (d,) = low.dirichlet
+    assert d.outputs["coeff"] == 1 and d.outputs["rhs"] == 0
+    non = lo.lower_nonlinear(problems.bratu(form_language), 2)
+    assert sympy.simplify(non.vertex[0].outputs["lin"] + 2 * lo.CV * sympy.exp(lo.UK0)) == 0
+    with pytest.raises(AssertionError):
+        lo.lower_linear(problems.bratu(form_language), 2)  # not linear in u
+
+
+def test_codegen_flags_and_factoring():
+    from pyfvm_b200 import codegen as cg
+    from pyfvm_b200 import form_language, lowering as lo
+
+    low = lo.lower_linear(problems.convection_diffusion(form_language), 2)
+    f = cg.generate(low, cg.MODE_LINEAR, [None], [None])
+    assert f.factored and f.uses_x and not f.uses_el and f.has_dirichlet
+    assert f.flags & cg.F_EDGE_D and not f.flags & cg.F_EDGE_C and not f.flags & cg.F_U
+    low = lo.lower_linear(problems.reaction_x(form_language), 2)
+    f = cg.generate(low, cg.MODE_LINEAR, [None], [None, None])
+    assert "x0_0" in f.source and "t0" in f.source or "x1_0" in f.source  # cse names never clash with x0_k
+    non = lo.lower_nonlinear(problems.bratu(form_language), 3)
+    r = cg.generate(non, cg.MODE_RESIDUAL, [None], [None])
+    j = cg.generate(non, cg.MODE_JACOBIAN, [None], [None])
+    assert r.flags & cg.F_EDGE_C and not r.flags & cg.F_EDGE_D and r.needs_u
+    assert j.flags & cg.F_EDGE_D and not j.flags & cg.F_EDGE_C
+    sub = lo.lower_linear(problems.subdomain_problem(form_language), 2)
+    ebits = [None if t.subdomain is None else 0 for t in sub.edge]
+    f = cg.generate(sub, cg.MODE_LINEAR, ebits, [None if t.subdomain is None else 0 for t in sub.vertex])
+    assert f.edge_masked and not f.factored and f.vert_masked  # per-half-edge masks forbid factoring
