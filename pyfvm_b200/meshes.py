@@ -158,6 +158,31 @@ class Mesh:
             self._boundary = mask
         return self._boundary
 
+    # -- output ---------------------------------------------------------------
+    def write(self, filename, point_data=None):
+        """``mesh.write("out.vtk", point_data={"x": x})`` [README:53, 123]: legacy ASCII
+        VTK unstructured grid (meshplex delegates to meshio; this stand-in writes
+        the one format the README uses)."""
+        if not str(filename).endswith(".vtk"):
+            raise ValueError("only legacy .vtk output is supported by this mesh stand-in")
+        pts, cells = self.node_coords, self.cells_points
+        k = cells.shape[1]
+        with open(filename, "w") as f:
+            f.write("# vtk DataFile Version 3.0\npyfvm_b200 mesh\nASCII\nDATASET UNSTRUCTURED_GRID\n")
+            f.write(f"POINTS {len(pts)} double\n")
+            numpy.savetxt(f, pts, fmt="%.17g")
+            f.write(f"CELLS {len(cells)} {len(cells) * (k + 1)}\n")
+            numpy.savetxt(f, numpy.column_stack([numpy.full(len(cells), k), cells]), fmt="%d")
+            f.write(f"CELL_TYPES {len(cells)}\n")
+            numpy.savetxt(f, numpy.full(len(cells), 5 if k == 3 else 10), fmt="%d")
+            if point_data:
+                f.write(f"POINT_DATA {len(pts)}\n")
+                for name, arr in point_data.items():
+                    arr = numpy.asarray(arr, dtype=numpy.float64)
+                    assert arr.shape == (len(pts),), "point_data arrays hold one value per vertex"
+                    f.write(f"SCALARS {name} double 1\nLOOKUP_TABLE default\n")
+                    numpy.savetxt(f, arr, fmt="%.17g")
+
     # -- subdomain masks ------------------------------------------------------
     def get_vertex_mask(self, subdomain=None):
         if subdomain is None:

@@ -128,6 +128,15 @@ class _DeviceProblem:
         m.has_canonical_format = True
         return m
 
+    def torch_pattern(self, device):
+        """(crow_indices, col_indices) as int32 torch tensors on ``device`` (cached)."""
+        import torch
+
+        if getattr(self, "_tpat", None) is None or self._tpat[0].device != device:
+            indptr, indices = self.dmesh.pattern()
+            self._tpat = (torch.from_numpy(indptr).to(device), torch.from_numpy(indices).to(device))
+        return self._tpat
+
     def upload_u(self, u):
         u = numpy.ascontiguousarray(u, dtype=numpy.float64)
         assert u.shape == (self.n,), "u must have one value per vertex"
@@ -149,6 +158,20 @@ class LinearProblem(_DeviceProblem):
         """Launch only; results stay in ``self.data`` / ``self.vec`` on the device."""
         self.launch(codegen.MODE_LINEAR, data_ptr=self.data.ptr, vec_ptr=self.vec.ptr)
 
+    def assemble_torch(self, device=None):
+        """``(matrix, rhs)`` as a ``torch.sparse_csr_tensor`` and a torch vector on the
+        GPU: the device-resident hand-off."""
+        import torch
+
+        device = device or torch.device("cuda", self.eng.device)
+        values = torch.empty(self.nnz, dtype=torch.float64, device=device)
+        rhs = torch.empty(self.n_rows, dtype=torch.float64, device=device)
+        torch.cuda.current_stream(device).synchronize()
+        self.launch(codegen.MODE_LINEAR, data_ptr=values.data_ptr(), vec_ptr=rhs.data_ptr())
+        self.eng.sync()
+        crow, col = self.torch_pattern(device)
+        return torch.sparse_csr_tensor(crow, col, values, size=(self.n_rows, self.n)), rhs
+
     def assemble(self, pinned=False):
         self.assemble_device()
         if pinned:
@@ -162,6 +185,39 @@ class LinearProblem(_DeviceProblem):
         return self.csr(data), rhs
 
 
+def _cuda_array(x):
+    """(device pointer, element count) of an object exposing ``__cuda_array_interface__``
+    (a torch / cupy array living on the GPU), or None for host arrays."""
+    cai = getattr(x, "__cuda_array_interface__", None)
+    if cai is None:
+        return None
+    assert cai["typestr"] in ("<f8", "=f8") and not cai.get("strides"), "contiguous float64 expected"
+    n = 1
+    for d in cai["shape"]:
+        n *= int(d)
+    return int(cai["data"][0]), n
+
+
+def _device_like(x, n):
+    """A new float64 device array of length n of the same library as ``x``."""
+    import torch  # the only __cuda_array_interface__ producer in this image
+
+    assert isinstance(x, torch.Tensor), "device outputs are returned as torch tensors"
+    return torch.empty(n, dtype=torch.float64, device=x.device)
+
+
+def _sync_producer(x):
+    """Work queued by the array's own library must be finished before the engine's
+    stream reads it (the engine runs on its own stream)."""
+    try:
+        import torch
+
+        if isinstance(x, torch.Tensor):
+            torch.cuda.current_stream(x.device).synchronize()
+    except ImportError:
+        pass
+
+
 class FvmProblem:
     """The residual ``f`` returned by ``discretize`` [README:110]."""
 
@@ -169,8 +225,19 @@ class FvmProblem:
         self._s = state
 
     def eval(self, u):
-        """``F(u)`` as a host array [README:121, 136]; ``u`` is a host array."""
+        """``F(u)`` [README:121, 136].  Host array in, host array out -- or, for an
+        array that already lives on the GPU (``__cuda_array_interface__``, e.g. a
+        torch CUDA tensor), device in, device out: nothing crosses PCIe."""
         s = self._s
+        dev = _cuda_array(u)
+        if dev is not None:
+            ptr, n = dev
+            assert n == s.n and ptr % 16 == 0, "u must hold one 16-byte aligned double per vertex"
+            _sync_producer(u)
+            out = _device_like(u, s.n_rows)
+            self.eval_device(ptr, out.data_ptr())
+            s.eng.sync()
+            return out
         self.eval_device(s.upload_u(u))
         out = numpy.empty(s.n_rows)
         s.vec.download(out)
@@ -200,6 +267,21 @@ class Jacobian:
     def values_device(self, u_ptr, out_ptr=None):
         s = self._s
         s.launch(codegen.MODE_JACOBIAN, u_ptr=u_ptr, data_ptr=out_ptr or s.data.ptr)
+
+    def get_linear_operator_torch(self, u):
+        """The Jacobian at ``u`` (a torch CUDA tensor) as a ``torch.sparse_csr_tensor`` on
+        the same device: pattern and values never leave HBM."""
+        import torch
+
+        s = self._s
+        ptr, n = _cuda_array(u)
+        assert n == s.n and ptr % 16 == 0
+        _sync_producer(u)
+        values = torch.empty(s.nnz, dtype=torch.float64, device=u.device)
+        self.values_device(ptr, values.data_ptr())
+        s.eng.sync()
+        crow, col = s.torch_pattern(u.device)
+        return torch.sparse_csr_tensor(crow, col, values, size=(s.n_rows, s.n))
 
 
 def discretize_linear(obj, mesh, device=None, fmad=False):

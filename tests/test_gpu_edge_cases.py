@@ -156,3 +156,32 @@ def test_piecewise_sqrt_pi_functors():
     parity.assert_vector_close(f.eval(u), F_ref, s["vec"])
     J_ref = j_ref.get_linear_operator(u, scales=s)
     parity.assert_matrix_close(j.get_linear_operator(u), J_ref, s["matrix"])
+
+
+def test_device_resident_handoff_torch():
+    """__cuda_array_interface__ in, torch tensors / sparse CSR out: same bits as the
+    host path, nothing crosses PCIe (SURVEY §8b proposal, §8f rank 4)."""
+    import torch
+
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import meshes, problem
+
+    mesh = meshes.Mesh(*meshes.jitter(*problems.rectangle(37, 23), scale=0.1, seed=8))
+    f, jac = eng.discretize(problems.nonlinear_conv(eng.form_language), mesh)
+    u = 0.3 * numpy.random.default_rng(4).standard_normal(len(mesh.points))
+    ut = torch.from_numpy(u).cuda()
+    Ft = f.eval(ut)
+    assert isinstance(Ft, torch.Tensor) and Ft.is_cuda
+    assert Ft.cpu().numpy().tobytes() == f.eval(u).tobytes()
+    Jt = jac.get_linear_operator_torch(ut)
+    J = jac.get_linear_operator(u)
+    assert Jt.values().cpu().numpy().tobytes() == J.data.tobytes()
+    assert numpy.array_equal(Jt.col_indices().cpu().numpy(), J.indices)
+    assert numpy.array_equal(Jt.crow_indices().cpu().numpy(), J.indptr)
+    lp = problem.LinearProblem(problems.convection_diffusion(eng.form_language), mesh)
+    At, bt = lp.assemble_torch()
+    A, b = lp.assemble()
+    assert At.values().cpu().numpy().tobytes() == A.data.tobytes()
+    assert bt.cpu().numpy().tobytes() == b.tobytes()
+    x = torch.from_numpy(u).cuda()
+    assert numpy.allclose((At @ x).cpu().numpy(), A @ u, rtol=1e-12, atol=1e-12)

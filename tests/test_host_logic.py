@@ -137,3 +137,15 @@ def test_codegen_flags_and_factoring():
     ebits = [None if t.subdomain is None else 0 for t in sub.edge]
     f = cg.generate(sub, cg.MODE_LINEAR, ebits, [None if t.subdomain is None else 0 for t in sub.vertex])
     assert f.edge_masked and not f.factored and f.vert_masked  # per-half-edge masks forbid factoring
+
+
+def test_vtk_output(tmp_path):
+    """mesh.write("out.vtk", point_data={"x": x}) [README:53]."""
+    from pyfvm_b200 import meshes
+
+    mesh = meshes.Mesh(*problems.rectangle(5, 4))
+    x = numpy.arange(20, dtype=float)
+    out = tmp_path / "out.vtk"
+    mesh.write(str(out), point_data={"x": x})
+    text = out.read_text()
+    assert "POINTS 20 double" in text and "CELLS 24 96" in text and "SCALARS x double 1" in text
