@@ -318,6 +318,21 @@ def run_ours(args):
         fun = s.functors[codegen.MODE_RESIDUAL]
         rb = algorithmic_bytes(R_local, nnz, n_rows, dm.dim, True, fun.uses_el, "residual")
         res = {"ms_per_eval": rms, "algorithmic_bytes": int(rb)}
+        if world == 1:
+            # f.eval(u) through the plugin object with host arrays, as scipy's
+            # newton_krylov [README:136] calls it: u up, F down, every evaluation
+            u_host = numpy.random.default_rng(0).standard_normal(part.n_local)
+            for i in range(2 + e2e_steps):
+                if i == 2:
+                    tf = time.time()
+                f.eval(u_host)
+            res["e2e_host_arrays"] = {
+                "value": R_global / ((time.time() - tf) / e2e_steps),
+                "unit": UNIT,
+                "h2d_bytes_per_step": 8 * part.n_local,
+                "d2h_bytes_per_step": 8 * n_rows,
+                "what": "f.eval(u) with pageable numpy arrays in and out",
+            }
 
     # ---- y = A x on the assembled system (the Krylov building block after the path)
     spmv = None
