@@ -13,7 +13,9 @@ third-party calls the reference used and that ARE installed here:
 ``sympy.lambdify``, ``numpy.add.at`` / ``subtract.at`` and
 ``scipy.sparse.coo_matrix(...).tocsr()`` (scipy 1.18.1, ``_coo.py:368-439``,
 ``_compressed.py:1072-1085``).  It is pinned only by the independent known
-answers in SURVEY §4 (``tests/test_oracle.py``, ``tests/golden/``).
+answers in SURVEY §4 (``tests/test_oracle.py``, ``tests/golden/``) and by
+second-order convergence to manufactured solutions (``tests/test_convergence.py``,
+the strategy of the reference's own test suite).
 
 The public surface mirrors the reference: ``discretize_linear``,
 ``discretize``, ``newton`` and the ``form_language`` module.
