@@ -334,8 +334,16 @@ def _mesh_arrays(mesh):
         mesh.node_coords if hasattr(mesh, "node_coords") else mesh.points, dtype=numpy.float64
     )
     dim = coords.shape[1]
-    if dim == 3 and not numpy.any(coords[:, 2]):
-        dim = 2  # planar mesh carried with a zero third column
+    if dim == 3:
+        planar = getattr(mesh, "_fvm_planar", None)
+        if planar is None:
+            planar = not numpy.any(coords[:, 2])
+            try:
+                mesh._fvm_planar = planar  # one pass over the coordinates per mesh object
+            except AttributeError:
+                pass
+        if planar:
+            dim = 2  # planar mesh carried with a zero third column
     return coords, dim
 
 
