@@ -239,6 +239,16 @@ int fvm_halo_push(fvm_ctx* ctx, const double* src_dev, const int32_t* send_index
  * returns instead of hanging. */
 int fvm_halo_wait(fvm_ctx* ctx, const uint64_t* const* flags_dev, int n_flags, uint64_t epoch,
                   double timeout_s, int32_t* timed_out_dev);
+/* fvm_assemble (residual / Jacobian modes) with the halo wait FUSED into the tile
+ * kernel: tiles are walked interior-first, and only a tile whose vertex table reaches
+ * into the ghost vertices makes the kernel's producer acquire every flags_dev[i]
+ * (>= epoch) before it copies u -- the NVLink transfer of the neighbours' pushes
+ * overlaps the interior math instead of a separate wait kernel.  Results are the
+ * same bits as fvm_halo_wait + fvm_assemble.  *timed_out_dev is set after ~20 s. */
+int fvm_assemble_halo(fvm_mesh* mesh, fvm_kernel* k, const uint8_t* vmask_dev,
+                      const uint8_t* dirid_dev, const double* u_dev, double* data_dev,
+                      double* vec_dev, const uint64_t* const* flags_dev, int n_flags, uint64_t epoch,
+                      int32_t* timed_out_dev);
 /* y += a*x (Newton update on the device) */
 int fvm_axpy(fvm_ctx* ctx, double a, const double* x_dev, double* y_dev, int64_t n);
 

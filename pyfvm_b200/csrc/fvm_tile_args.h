@@ -86,6 +86,16 @@ struct FvmTileArgs {
   const double* mat;               // [nnz] CSR values to multiply with (SpMV mode)
   double* data;                    // [nnz] CSR values out (assembly / Jacobian modes)
   double* vec;                     // [nrows] rhs (assembly) or F (residual) out
+  // fused halo wait (row-partitioned runs): a tile whose vertex table reaches into the
+  // ghost vertices [0, ghost_lo_end) or [ghost_hi_begin, nverts) makes the producer
+  // acquire every neighbour's epoch flag before it copies u; tiles are walked starting
+  // at tile_rot (interior first), so the NVLink transfer hides behind the interior math
+  const unsigned long long* const* halo_flags;  // [n_halo_flags] flag words (or null)
+  unsigned long long halo_epoch;
+  int* halo_timeout;               // set to 1 when a wait gives up (never hangs)
+  int n_halo_flags;
+  int ghost_lo_end, ghost_hi_begin;
+  int tile_rot;
   int row_base;                    // local vertex id of row 0 (row partitioning)
   int ntiles;
   int max_he;                      // largest tile: half-edges

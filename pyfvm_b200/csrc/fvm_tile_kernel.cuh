@@ -145,9 +145,32 @@ __device__ __forceinline__ unsigned fvm_shift_at(long long index, unsigned elem_
   return ((unsigned)index * elem_bytes) & 15u;
 }
 
+// Fused halo wait: spin (with back-off) until every neighbour has released this epoch
+// into its flag word -- the ghost values it pushed over NVLink are then in our HBM --
+// and order the bulk copies (async proxy) after the acquire.  Gives up after ~20 s.
+__device__ __noinline__ void fvm_halo_acquire(const FvmTileArgs& a) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int i = 0; i < a.n_halo_flags; ++i) {
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.halo_flags[i]) : "memory");
+      if (v >= a.halo_epoch) break;
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) {
+        *a.halo_timeout = 1;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemLayout& L,
                                             unsigned char* stage, void* full,
-                                            const FvmTileDesc& d) {
+                                            const FvmTileDesc& d, bool& halo_ready) {
   const int v0 = a.row_base + d.r0;
   *(FvmTileDesc*)(stage + L.desc) = d;
   unsigned total = 0;
@@ -229,6 +252,18 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
 #endif
 #if FVM_STAGE_U
   {
+    if (a.n_halo_flags > 0 && !halo_ready) {
+      // does this tile's vertex table reach into the ghost vertices?
+      int tmin = d.own_start, tmax = d.own_start + d.own_count;
+      if (nhalo > 0) {
+        tmin = min(tmin, sd->hstart[0]);
+        tmax = max(tmax, sd->hstart[nhalo - 1] + (int)sd->hcount[nhalo - 1]);
+      }
+      if (tmin < a.ghost_lo_end || tmax > a.ghost_hi_begin) {
+        fvm_halo_acquire(a);
+        halo_ready = true;
+      }
+    }
     unsigned char* dst = stage + L.u;
     if (d.own_count) fvm_bulk_g2s(dst, a.u + d.own_start, (unsigned)d.own_count * 8u, full);
     dst += (unsigned)d.own_count * 8u;
@@ -314,14 +349,17 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
     if (threadIdx.x == 0) {
       int t = blockIdx.x;
       if (t < a.ntiles) {
-        FvmTileDesc d = fvm_load_desc(a.tiles + t);
+        // tile t of the walk is tile (t + tile_rot) mod ntiles of the mesh
+        auto rot = [&](int i) { return i + a.tile_rot < a.ntiles ? i + a.tile_rot : i + a.tile_rot - a.ntiles; };
+        bool halo_ready = false;
+        FvmTileDesc d = fvm_load_desc(a.tiles + rot(t));
         for (int it = 0; t < a.ntiles; ++it) {
           const int st = it % FVM_STAGES;
           const int tn = t + gridDim.x;
           FvmTileDesc dn = d;
-          if (tn < a.ntiles) dn = fvm_load_desc(a.tiles + tn);  // next descriptor in flight
+          if (tn < a.ntiles) dn = fvm_load_desc(a.tiles + rot(tn));  // next descriptor in flight
           if (it >= FVM_STAGES) fvm_mbar_wait(empty + st, ((it / FVM_STAGES) - 1) & 1);
-          fvm_produce(a, L, sm + L.stage0 + st * L.stage_bytes, full + st, d);
+          fvm_produce(a, L, sm + L.stage0 + st * L.stage_bytes, full + st, d, halo_ready);
           d = dn;
           t = tn;
         }

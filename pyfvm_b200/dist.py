@@ -308,10 +308,19 @@ class PeerHalo:
         """Buffer index the next exchange will use (owned part to be filled first)."""
         return (self.epoch + 1) & 1
 
-    def exchange(self):
+    def fused_wait(self):
+        """Argument tuple that makes the next tile-kernel launch wait for this epoch's
+        pushes inside the kernel (``fvm_assemble_halo``); None without neighbours."""
+        if not self.n_flags:
+            return None
+        return (self.flag_ptrs.ptr, self.n_flags, self.epoch, self.timeout_ptr)
+
+    def exchange(self, wait=True):
         """Push my owned boundary values of buffer ``next_buffer()`` to the
-        neighbours, wait for theirs; returns the device address of the complete
-        local ``u``.  Everything is stream-ordered on the ctx stream."""
+        neighbours and -- ``wait=True`` -- wait for theirs with a stream-ordered
+        kernel; with ``wait=False`` the consumer launch waits itself
+        (``fused_wait()``).  Returns the device address of the local ``u``.
+        Everything is stream-ordered on the ctx stream."""
         eng, lib = self.eng, self.eng.lib
         self.epoch += 1
         k = self.epoch & 1
@@ -319,7 +328,7 @@ class PeerHalo:
         for p, d in sorted(self.peer.items()):
             dst = d["base"] + k * d["ustride"] + d["ghost_byte_off"]
             eng._ck(lib.fvm_halo_push(eng.ctx, src, d["send"].ptr, d["n"], dst, d["flag"], self.epoch))
-        if self.n_flags:
+        if self.n_flags and wait:
             eng._ck(
                 lib.fvm_halo_wait(
                     eng.ctx, self.flag_ptrs.ptr, self.n_flags, self.epoch, self.TIMEOUT_S,
@@ -364,10 +373,17 @@ class DistributedFvm:
     """``pyfvm.discretize`` on one rank of a row partition: ``eval(u_owned)`` and
     ``jacobian_values(u_owned)`` exchange the ghost values first."""
 
-    def __init__(self, obj, part, halo="peer", device=None, fmad=False, group=None):
+    def __init__(self, obj, part, halo="peer", device=None, fmad=False, group=None, fused=True):
+        """``halo``: "peer" (CUDA-IPC pushes) or "torch" (NCCL send/recv).  ``fused``
+        (peer only): the tile kernel itself waits for the neighbours' pushes, and only
+        where a tile touches ghost vertices, instead of a wait kernel in front of it."""
         from .problem import _DeviceProblem
 
         self.part = part
+        import os
+
+        fused = int(os.environ.get("FVM_FUSED_HALO", "1" if fused else "0"))  # experiments
+        self.fused = bool(fused) and halo == "peer"
         self.s = _DeviceProblem(
             obj, part.mesh, "nonlinear", device=device, fmad=fmad, row_range=part.row_range
         )
@@ -403,18 +419,25 @@ class DistributedFvm:
     def exchange(self):
         """Ghost values in place; returns the device address of the local ``u``."""
         if self.kind == "peer":
-            return self.halo.exchange()
+            return self.halo.exchange(wait=not self.fused)
         import torch
 
         self.halo.exchange(self.u_t)
         torch.cuda.current_stream().synchronize()  # NCCL stream -> ctx stream hand-off
         return self.u_t.data_ptr()
 
+    def _halo_arg(self, mode):
+        if not self.fused or not self.s.functors[mode].needs_u:
+            return None
+        return self.halo.fused_wait()
+
     def residual_device(self, u_ptr):
-        self.s.launch(codegen.MODE_RESIDUAL, u_ptr=u_ptr, vec_ptr=self.F.ptr)
+        self.s.launch(codegen.MODE_RESIDUAL, u_ptr=u_ptr, vec_ptr=self.F.ptr,
+                      halo=self._halo_arg(codegen.MODE_RESIDUAL))
 
     def jacobian_device(self, u_ptr):
-        self.s.launch(codegen.MODE_JACOBIAN, u_ptr=u_ptr, data_ptr=self.s.data.ptr)
+        self.s.launch(codegen.MODE_JACOBIAN, u_ptr=u_ptr, data_ptr=self.s.data.ptr,
+                      halo=self._halo_arg(codegen.MODE_JACOBIAN))
 
     # -- host API ---------------------------------------------------------------
     def eval(self, u_owned):

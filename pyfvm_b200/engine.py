@@ -131,6 +131,11 @@ SYMBOLS = {
         c_int,
         [c_void_p, c_void_p, c_int, ctypes.c_uint64, c_double, c_void_p],
     ),
+    "fvm_assemble_halo": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+         ctypes.c_uint64, c_void_p],
+    ),
     "fvm_axpy": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_int64]),
 }
 
@@ -487,11 +492,21 @@ class DeviceMesh:
             self.eng.lib.fvm_mesh_update_geometry(self.handle, *[_ptr(a) for a in arrs], 0)
         )
 
-    def launch(self, kernel, vmask=None, dirid=None, u=None, data=None, vec=None):
-        """One tile-kernel launch; all arguments are device addresses (int) or None."""
-        self.eng._ck(
-            self.eng.lib.fvm_assemble(self.handle, kernel.handle, vmask, dirid, u, data, vec)
-        )
+    def launch(self, kernel, vmask=None, dirid=None, u=None, data=None, vec=None, halo=None):
+        """One tile-kernel launch; all arguments are device addresses (int) or None.
+        ``halo = (flag pointer array, count, epoch, timeout flag)``: the launch waits for
+        the neighbours' pushes inside the kernel (``fvm_assemble_halo``)."""
+        if halo is not None:
+            flags, n, epoch, tout = halo
+            self.eng._ck(
+                self.eng.lib.fvm_assemble_halo(
+                    self.handle, kernel.handle, vmask, dirid, u, data, vec, flags, n, epoch, tout
+                )
+            )
+        else:
+            self.eng._ck(
+                self.eng.lib.fvm_assemble(self.handle, kernel.handle, vmask, dirid, u, data, vec)
+            )
         self.eng.launches += 1
 
 

@@ -108,7 +108,7 @@ class _DeviceProblem:
     def _p(self, buf):
         return None if buf is None else buf.ptr
 
-    def launch(self, mode, u_ptr=None, data_ptr=None, vec_ptr=None):
+    def launch(self, mode, u_ptr=None, data_ptr=None, vec_ptr=None, halo=None):
         self.dmesh.launch(
             self.kernels[mode],
             vmask=self._p(self.vmask),
@@ -116,6 +116,7 @@ class _DeviceProblem:
             u=u_ptr,
             data=data_ptr,
             vec=vec_ptr,
+            halo=halo,
         )
 
     def csr(self, data_host):

@@ -91,14 +91,14 @@ def gpu_worker():
             rng = numpy.random.default_rng(3)
             us = [0.3 * rng.standard_normal(nglob) for _ in range(3)]
             results = {}
-            for halo in ("peer", "torch"):
-                dp = fd.DistributedFvm(prob, part, halo=halo)
+            for halo in ("peer", "peer-unfused", "torch"):
+                dp = fd.DistributedFvm(prob, part, halo=halo.split("-")[0], fused=halo == "peer")
                 Fs, Js = [], []
                 for u in us:  # several epochs: exercises the double buffering
                     Fs.append(dp.eval(part.owned(u)))
                     Js.append(dp.jacobian_values(part.owned(u)))
                 results[halo] = (Fs, Js)
-                if halo == "peer":
+                if halo.startswith("peer"):
                     dist.barrier()
                     dp.halo.close()
             A_loc, b_loc = fd.discretize_linear(
@@ -115,7 +115,7 @@ def gpu_worker():
             if rank == 0:
                 f1, j1 = eng.discretize(prob, mesh)
                 A1, b1 = eng.discretize_linear(problems.convection_diffusion(eng.form_language), mesh)
-                for h in ("peer", "torch"):
+                for h in ("peer", "peer-unfused", "torch"):
                     for k, u in enumerate(us):
                         F = b"".join(g[h][0][k] for g in gathered)
                         Jd = b"".join(g[h][1][k] for g in gathered)
