@@ -205,6 +205,12 @@ int fvm_assemble(fvm_mesh* mesh, fvm_kernel* k, const uint8_t* vmask_dev,
 int fvm_spmv_kernel_create(fvm_ctx* ctx, fvm_kernel** out);
 int fvm_spmv(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* values_dev, const double* x_dev,
              double* y_dev);
+/* row-partitioned y = A x: x_dev holds the local vector (ghost | owned | ghost); the
+ * kernel waits for the neighbours' pushes of the ghost entries itself (see
+ * fvm_assemble_halo) */
+int fvm_spmv_halo(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* values_dev,
+                  const double* x_dev, double* y_dev, const uint64_t* const* flags_dev,
+                  int n_flags, uint64_t epoch, int32_t* timed_out_dev);
 /* diag_dev[r] = A[r, r] (Jacobi preconditioner) */
 int fvm_csr_diagonal(fvm_mesh* mesh, const double* values_dev, double* diag_dev);
 /* deterministic dot product (fixed-shape two-stage reduction), z = a x + b y, z = x / d */

@@ -114,6 +114,10 @@ SYMBOLS = {
     ),
     "fvm_spmv_kernel_create": (c_int, [c_void_p, POINTER(c_void_p)]),
     "fvm_spmv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fvm_spmv_halo": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_uint64, c_void_p],
+    ),
     "fvm_csr_diagonal": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fvm_dot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double)]),
     "fvm_axpby": (c_int, [c_void_p, c_double, c_void_p, c_double, c_void_p, c_void_p, c_int64]),

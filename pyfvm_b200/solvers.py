@@ -20,10 +20,12 @@ from . import codegen
 class DeviceSystem:
     """``A`` = (pattern of a device mesh, CSR values in HBM) for square systems."""
 
-    def __init__(self, dmesh, values_ptr):
-        assert dmesh.n_rows == dmesh.n and dmesh.row_base == 0, "single-GPU square systems only"
+    def __init__(self, dmesh, values_ptr, _partitioned=False):
+        assert _partitioned or (dmesh.n_rows == dmesh.n and dmesh.row_base == 0), (
+            "square single-GPU systems; row partitions use DistributedSystem"
+        )
         self.dmesh, self.eng, self.values = dmesh, dmesh.eng, values_ptr
-        self.n = dmesh.n
+        self.n = dmesh.n_rows  # length of the vectors the solver works on (owned rows)
         eng = self.eng
         if getattr(eng, "_spmv_kernel", None) is None:
             h = c_void_p()
@@ -50,6 +52,9 @@ class DeviceSystem:
         self.eng._ck(self.eng.lib.fvm_dot(self.eng.ctx, x, y, self.n, byref(out)))
         return out.value
 
+    def _norm(self, x):
+        return self.eng.norm2(x, self.n)
+
     def _axpby(self, a, x, b, y, z):
         self.eng._ck(self.eng.lib.fvm_axpby(self.eng.ctx, a, x, b, y, z, self.n))
 
@@ -64,7 +69,7 @@ class DeviceSystem:
             self._work = [e.alloc(8 * n + 16) for _ in range(8)]
         r, r0, p, v, s, t, ph, sh = (w.ptr for w in self._work)
         d = self.diagonal().ptr
-        bnorm = e.norm2(b_ptr, n)
+        bnorm = self._norm(b_ptr)
         if bnorm == 0.0:
             e._ck(lib.fvm_dev_memset(e.ctx, x_ptr, 0, 8 * n))
             return 0, 0.0
@@ -78,7 +83,7 @@ class DeviceSystem:
         e._ck(lib.fvm_dev_memset(e.ctx, p, 0, 8 * n))
         e._ck(lib.fvm_dev_memset(e.ctx, v, 0, 8 * n))
         rho = alpha = omega = 1.0
-        res = e.norm2(r, n)
+        res = self._norm(r)
         for it in range(1, maxiter + 1):
             if res <= tol * bnorm:
                 return it - 1, res / bnorm
@@ -95,7 +100,7 @@ class DeviceSystem:
                 raise ArithmeticError("BiCGStab breakdown")
             alpha = rho_new / r0v
             self._axpby(1.0, r, -alpha, v, s)
-            res = e.norm2(s, n)
+            res = self._norm(s)
             if res <= tol * bnorm:
                 self._axpby(1.0, x_ptr, alpha, ph, x_ptr)
                 return it, res / bnorm
@@ -108,7 +113,7 @@ class DeviceSystem:
             self._axpby(1.0, x_ptr, alpha, ph, x_ptr)
             self._axpby(1.0, x_ptr, omega, sh, x_ptr)
             self._axpby(1.0, s, -omega, t, r)
-            res = e.norm2(r, n)
+            res = self._norm(r)
             rho = rho_new
         if res <= tol * bnorm:
             return maxiter, res / bnorm
@@ -172,3 +177,95 @@ def newton_device(f, jacobian, u0, tol=1e-10, max_iter=20, lin_tol=1e-10, verbos
     out = numpy.empty(n)
     s.u.download(out)
     return out, steps
+
+
+class DistributedSystem(DeviceSystem):
+    """The row-partitioned system of a :class:`pyfvm_b200.dist.DistributedFvm`: every
+    rank holds its owned rows; vectors are the owned parts.  ``matvec`` pushes the
+    owned boundary entries of x to the neighbours over NVLink peer memory and the
+    SpMV kernel waits for theirs itself (``fvm_spmv_halo``); dot products are the
+    deterministic local sums plus one all-reduce of a double."""
+
+    def __init__(self, dp, values_ptr=None, group=None):
+        import torch
+
+        from .dist import PeerHalo
+
+        super().__init__(dp.s.dmesh, values_ptr or dp.s.data.ptr, _partitioned=True)
+        self.dp, self.part, self.group = dp, dp.part, group
+        self.vhalo = PeerHalo(dp.part, self.eng, group=group)  # its own buffers / flags
+        self._red = torch.zeros(1, dtype=torch.float64, device=f"cuda:{self.eng.device}")
+
+    def _allreduce(self, v):
+        if self.part.world == 1:
+            return v
+        import torch.distributed as dist
+
+        self._red[0] = v
+        dist.all_reduce(self._red, group=self.group)
+        return float(self._red.item())
+
+    def _dot(self, x, y):
+        return self._allreduce(super()._dot(x, y))
+
+    def _norm(self, x):
+        return numpy.sqrt(self._allreduce(self.eng.norm2(x, self.n) ** 2))
+
+    def matvec(self, x_ptr, y_ptr):
+        e, h = self.eng, self.vhalo
+        dst = h.u_ptr(h.next_buffer()) + 8 * self.part.n_ghost_lo
+        self._axpby(1.0, x_ptr, 0.0, x_ptr, dst)  # owned part into the exchange buffer
+        xl = h.exchange(wait=False)
+        fw = h.fused_wait()
+        if fw is None:
+            e._ck(e.lib.fvm_spmv(self.dmesh.handle, e._spmv_kernel, self.values, xl, y_ptr))
+        else:
+            e._ck(e.lib.fvm_spmv_halo(self.dmesh.handle, e._spmv_kernel, self.values, xl, y_ptr, *fw))
+        e.launches += 1
+
+    def close(self):
+        self.vhalo.close()
+
+
+def newton_distributed(dp, u0_owned, tol=1e-10, max_iter=20, lin_tol=1e-10, verbose=False, group=None):
+    """``pyfvm.newton`` [README:121] on a row partition (one rank per GPU): residual,
+    Jacobian refresh, BiCGStab and update stay in HBM; per step a handful of
+    doubles cross NCCL (norms / dot products) and the ghost values cross NVLink.
+    Returns (owned part of the solution, steps, total BiCGStab iterations)."""
+    e, part = dp.eng, dp.part
+    n = part.n_owned
+    sysm = DistributedSystem(dp, group=group)
+    du = e.alloc(8 * max(1, n))
+    off = 8 * part.n_ghost_lo
+    assert dp.kind == "peer", "newton_distributed drives the peer-memory halo"
+    dp.set_owned(u0_owned)
+    u_ptr = dp.exchange()
+    steps = lin_its = 0
+    try:
+        while True:
+            dp.residual_device(u_ptr)
+            nrm = sysm._norm(dp.F.ptr)
+            if verbose and part.rank == 0:
+                print(f"||F(u)|| = {nrm:e}", flush=True)
+            if nrm < tol:
+                break
+            if steps >= max_iter:
+                raise RuntimeError(f"Newton did not converge in {max_iter} steps (||F|| = {nrm:e})")
+            dp.jacobian_device(u_ptr)
+            its, _ = sysm.bicgstab(dp.F.ptr, du.ptr, tol=lin_tol, x0_is_zero=True)
+            lin_its += its
+            nxt = dp.halo.u_ptr(dp.halo.next_buffer()) + off
+            sysm._axpby(1.0, u_ptr + off, -1.0, du.ptr, nxt)  # u_new = u - du, owned part
+            u_ptr = dp.exchange()
+            steps += 1
+        out = numpy.empty(n)
+        e._ck(e.lib.fvm_d2h(e.ctx, out.ctypes.data, u_ptr + off, out.nbytes))
+        dp.halo.check_timeout()
+        sysm.vhalo.check_timeout()
+    finally:
+        if part.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=group)
+        sysm.close()
+    return out, steps, lin_its

@@ -135,6 +135,26 @@ def gpu_worker():
                 )
                 print(f"{kind} linear assembly: bit-identical={lin}", flush=True)
                 ok &= lin
+        # distributed Newton (Bratu) with the device BiCGStab vs the single-GPU device Newton
+        from pyfvm_b200 import solvers
+
+        mesh = _mesh("cube", 13)
+        part = fd.Partition(mesh, rank, world)
+        prob = problems.bratu(eng.form_language)
+        dp = fd.DistributedFvm(prob, part, halo="peer")
+        u_own, steps, its = solvers.newton_distributed(dp, numpy.zeros(part.n_owned))
+        pieces = [None] * world
+        dist.all_gather_object(pieces, u_own)
+        dist.barrier()
+        dp.halo.close()
+        if rank == 0:
+            f1, j1 = eng.discretize(prob, mesh)
+            u1, steps1 = solvers.newton_device(f1, j1, numpy.zeros(len(mesh.points)))
+            err = numpy.abs(numpy.concatenate(pieces) - u1).max()
+            good = steps == steps1 and err <= 1e-8
+            print(f"distributed Newton: steps={steps} (1 GPU: {steps1}), BiCGStab its={its}, "
+                  f"max |u - u_1gpu| = {err:.2e}: ok={good}", flush=True)
+            ok &= good
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.broadcast(flag, 0)
         ok = bool(flag.item())
