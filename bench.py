@@ -579,6 +579,33 @@ def run_c5(args):
         "pattern_build_ms": dm.build_ms,
         "setup_s": setup_s,
     }
+    if args.solve:
+        # the whole nonlinear solve on the partition: pyfvm.newton's loop with the device
+        # BiCGStab (Jacobi) as jacobian_solver; nothing per-record or per-slot leaves HBM
+        from pyfvm_b200 import solvers
+
+        barrier()
+        ts = time.time()
+        u_own, steps, lin_its = solvers.newton_distributed(
+            dp, numpy.zeros(part.n_owned), tol=args.newton_tol, lin_tol=1e-8, verbose=(rank == 0)
+        )
+        barrier()
+        umax = float(u_own.max()) if len(u_own) else 0.0
+        if dist is not None:
+            import torch
+
+            t = torch.tensor([umax], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            umax = float(t.item())
+        out["newton_solve"] = {
+            "seconds": time.time() - ts,
+            "newton_steps": steps,
+            "bicgstab_iterations": lin_its,
+            "tol": args.newton_tol,
+            "max_u": umax,
+            "what": "pyfvm.newton from u = 0 with a Jacobi-BiCGStab jacobian_solver, residual / "
+            "Jacobian refresh / SpMV / updates in HBM across the ranks",
+        }
     if rank == 0:
         print(json.dumps(out), flush=True)
     if dist is not None:
@@ -682,6 +709,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
                     help="c4: BASELINE config 4 (default, the headline); c5: Bratu on cube_tetra slabs")
     ap.add_argument("--cube", type=int, default=200, help="points per side of the c5 cube")
+    ap.add_argument("--solve", action="store_true", help="c5: also run the full Newton solve")
+    ap.add_argument("--newton-tol", type=float, default=1e-10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
