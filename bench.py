@@ -584,6 +584,7 @@ def run_c5(args):
         # BiCGStab (Jacobi) as jacobian_solver; nothing per-record or per-slot leaves HBM
         from pyfvm_b200 import solvers
 
+        solvers.DeviceSystem(dm, s.data.ptr, _partitioned=True)  # NVRTC-compiles the SpMV kernel
         barrier()
         ts = time.time()
         u_own, steps, lin_its = solvers.newton_distributed(

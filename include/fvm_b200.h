@@ -215,6 +215,9 @@ int fvm_spmv_halo(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* values_
 int fvm_csr_diagonal(fvm_mesh* mesh, const double* values_dev, double* diag_dev);
 /* deterministic dot product (fixed-shape two-stage reduction), z = a x + b y, z = x / d */
 int fvm_dot(fvm_ctx* ctx, const double* x_dev, const double* y_dev, int64_t n, double* out);
+/* out2[0] = x1 . y1, out2[1] = x2 . y2 in one pass and one host synchronisation */
+int fvm_dot2(fvm_ctx* ctx, const double* x1_dev, const double* y1_dev, const double* x2_dev,
+             const double* y2_dev, int64_t n, double* out2);
 int fvm_axpby(fvm_ctx* ctx, double a, const double* x_dev, double b, const double* y_dev,
               double* z_dev, int64_t n);
 int fvm_vdiv(fvm_ctx* ctx, const double* x_dev, const double* d_dev, double* z_dev, int64_t n);

@@ -120,6 +120,9 @@ SYMBOLS = {
     ),
     "fvm_csr_diagonal": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fvm_dot": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double)]),
+    "fvm_dot2": (
+        c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double)],
+    ),
     "fvm_axpby": (c_int, [c_void_p, c_double, c_void_p, c_double, c_void_p, c_void_p, c_int64]),
     "fvm_vdiv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
     "fvm_norm2": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double)]),

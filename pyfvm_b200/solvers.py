@@ -55,6 +55,12 @@ class DeviceSystem:
     def _norm(self, x):
         return self.eng.norm2(x, self.n)
 
+    def _dot2(self, x1, y1, x2, y2):
+        """(x1.y1, x2.y2) with one host synchronisation."""
+        out = (c_double * 2)()
+        self.eng._ck(self.eng.lib.fvm_dot2(self.eng.ctx, x1, y1, x2, y2, self.n, out))
+        return out[0], out[1]
+
     def _axpby(self, a, x, b, y, z):
         self.eng._ck(self.eng.lib.fvm_axpby(self.eng.ctx, a, x, b, y, z, self.n))
 
@@ -83,11 +89,12 @@ class DeviceSystem:
         e._ck(lib.fvm_dev_memset(e.ctx, p, 0, 8 * n))
         e._ck(lib.fvm_dev_memset(e.ctx, v, 0, 8 * n))
         rho = alpha = omega = 1.0
-        res = self._norm(r)
+        # three reductions per iteration: r0.v | (t.s, t.t) | (r0.r, r.r)
+        rho_new, rr = self._dot2(r0, r, r, r)
+        res = numpy.sqrt(rr)
         for it in range(1, maxiter + 1):
             if res <= tol * bnorm:
                 return it - 1, res / bnorm
-            rho_new = self._dot(r0, r)
             if rho_new == 0.0 or omega == 0.0:
                 raise ArithmeticError("BiCGStab breakdown")
             beta = (rho_new / rho) * (alpha / omega)
@@ -100,21 +107,17 @@ class DeviceSystem:
                 raise ArithmeticError("BiCGStab breakdown")
             alpha = rho_new / r0v
             self._axpby(1.0, r, -alpha, v, s)
-            res = self._norm(s)
-            if res <= tol * bnorm:
-                self._axpby(1.0, x_ptr, alpha, ph, x_ptr)
-                return it, res / bnorm
             e._ck(lib.fvm_vdiv(e.ctx, s, d, sh, n))
             self.matvec(sh, t)
-            tt = self._dot(t, t)
-            if tt == 0.0:
-                raise ArithmeticError("BiCGStab breakdown")
-            omega = self._dot(t, s) / tt
+            ts, tt = self._dot2(t, s, t, t)
+            # t = 0 means s = 0: the half step already solved the system
+            omega = ts / tt if tt != 0.0 else 0.0
             self._axpby(1.0, x_ptr, alpha, ph, x_ptr)
             self._axpby(1.0, x_ptr, omega, sh, x_ptr)
             self._axpby(1.0, s, -omega, t, r)
-            res = self._norm(r)
             rho = rho_new
+            rho_new, rr = self._dot2(r0, r, r, r)
+            res = numpy.sqrt(rr)
         if res <= tol * bnorm:
             return maxiter, res / bnorm
         raise ArithmeticError(f"BiCGStab did not converge: relative residual {res / bnorm:.3e}")
@@ -195,6 +198,7 @@ class DistributedSystem(DeviceSystem):
         self.dp, self.part, self.group = dp, dp.part, group
         self.vhalo = PeerHalo(dp.part, self.eng, group=group)  # its own buffers / flags
         self._red = torch.zeros(1, dtype=torch.float64, device=f"cuda:{self.eng.device}")
+        self._red2 = torch.zeros(2, dtype=torch.float64, device=f"cuda:{self.eng.device}")
 
     def _allreduce(self, v):
         if self.part.world == 1:
@@ -210,6 +214,18 @@ class DistributedSystem(DeviceSystem):
 
     def _norm(self, x):
         return numpy.sqrt(self._allreduce(self.eng.norm2(x, self.n) ** 2))
+
+    def _dot2(self, x1, y1, x2, y2):
+        a, b = super()._dot2(x1, y1, x2, y2)
+        if self.part.world == 1:
+            return a, b
+        import torch
+        import torch.distributed as dist
+
+        self._red2[0], self._red2[1] = a, b
+        dist.all_reduce(self._red2, group=self.group)
+        a, b = self._red2.tolist()
+        return a, b
 
     def matvec(self, x_ptr, y_ptr):
         e, h = self.eng, self.vhalo
