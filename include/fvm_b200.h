@@ -222,6 +222,15 @@ int fvm_axpby(fvm_ctx* ctx, double a, const double* x_dev, double b, const doubl
               double* z_dev, int64_t n);
 int fvm_vdiv(fvm_ctx* ctx, const double* x_dev, const double* d_dev, double* z_dev, int64_t n);
 
+/* Jacobi-preconditioned BiCGStab for A x = b (x0 = 0) with every scalar resident in HBM:
+ * one iteration (2 SpMV launches of the tile kernel, 3 fused vector kernels, 3 two-stage
+ * reductions, 3 scalar steps) is captured once in a CUDA graph and replayed; the host
+ * reads the residual every check_every iterations only.  work_dev: 9 * ((n+1)&~1) + 16
+ * doubles.  Stops at ||r|| <= tol ||b||; fails on breakdown / maxiter. */
+int fvm_bicgstab(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* values_dev,
+                 const double* b_dev, double* x_dev, double* work_dev, double tol, int maxiter,
+                 int check_every, int* iters_out, double* relres_out);
+
 /* ---- small device helpers used around the path --------------------------------*/
 /* deterministic ||x||_2 (fixed-shape two-stage reduction) [README.md:121 newton] */
 int fvm_norm2(fvm_ctx* ctx, const double* x_dev, int64_t n, double* out);

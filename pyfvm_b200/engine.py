@@ -125,6 +125,11 @@ SYMBOLS = {
     ),
     "fvm_axpby": (c_int, [c_void_p, c_double, c_void_p, c_double, c_void_p, c_void_p, c_int64]),
     "fvm_vdiv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
+    "fvm_bicgstab": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int,
+         POINTER(c_int), POINTER(c_double)],
+    ),
     "fvm_norm2": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double)]),
     "fvm_gather_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "fvm_ipc_export": (c_int, [c_void_p, c_void_p, c_char_p]),

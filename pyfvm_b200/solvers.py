@@ -64,11 +64,35 @@ class DeviceSystem:
     def _axpby(self, a, x, b, y, z):
         self.eng._ck(self.eng.lib.fvm_axpby(self.eng.ctx, a, x, b, y, z, self.n))
 
-    def bicgstab(self, b_ptr, x_ptr, tol=1e-10, maxiter=None, x0_is_zero=False):
+    def bicgstab_graph(self, b_ptr, x_ptr, tol=1e-10, maxiter=None, check_every=16):
+        """``A x = b`` from x0 = 0 with ``fvm_bicgstab``: all scalars stay in HBM and one
+        iteration is a CUDA graph replayed ``check_every`` times between host looks at
+        the residual (single-GPU systems)."""
+        e, n = self.eng, self.n
+        maxiter = maxiter or 20 * int(numpy.sqrt(n)) + 200
+        if getattr(self, "_gwork", None) is None:
+            self._gwork = e.alloc(8 * (9 * ((n + 1) & ~1) + 16))
+        its, rel = ctypes.c_int(), c_double()
+        rc = e.lib.fvm_bicgstab(
+            self.dmesh.handle, e._spmv_kernel, self.values, b_ptr, x_ptr, self._gwork.ptr, tol,
+            maxiter, check_every, byref(its), byref(rel),
+        )
+        if rc != 0:
+            msg = e.lib.fvm_last_error().decode()
+            if "BiCGStab" in msg:
+                raise ArithmeticError(f"{msg}: relative residual {rel.value:.3e}")
+            e._ck(rc)
+        e.launches += 2 * its.value
+        return its.value, rel.value
+
+    def bicgstab(self, b_ptr, x_ptr, tol=1e-10, maxiter=None, x0_is_zero=False, graph=True):
         """Solve ``A x = b`` (device pointers), right-preconditioned with the
         diagonal.  Stops at ``||r|| <= tol * ||b||``.  Returns (iterations,
         relative residual); raises ``ArithmeticError`` on breakdown or no
-        convergence."""
+        convergence.  From x0 = 0 on one GPU the device-resident, graph-replayed
+        ``fvm_bicgstab`` does the work; otherwise this host-driven loop."""
+        if graph and x0_is_zero and type(self) is DeviceSystem:
+            return self.bicgstab_graph(b_ptr, x_ptr, tol=tol, maxiter=maxiter)
         e, lib, n = self.eng, self.eng.lib, self.n
         maxiter = maxiter or 20 * int(numpy.sqrt(n)) + 200
         if self._work is None:

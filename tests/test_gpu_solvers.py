@@ -85,3 +85,28 @@ def test_newton_with_device_jacobian_solver_and_device_newton():
     assert u_host.max() == pytest.approx(0.28395, abs=1e-5)
     assert numpy.abs(u_cb - u_host).max() <= 1e-8
     assert numpy.abs(u_dev - u_host).max() <= 1e-8
+
+
+def test_graph_bicgstab_matches_host_driven_loop():
+    """fvm_bicgstab (device scalars, CUDA-graph iterations) against the host-driven loop."""
+    import time
+
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import meshes, problem, solvers
+
+    mesh = meshes.Mesh(*problems.rectangle(151, 77))
+    lp = problem.LinearProblem(problems.convection_diffusion(eng.form_language), mesh)
+    lp.assemble_device()
+    sysm = solvers.DeviceSystem(lp.dmesh, lp.data.ptr)
+    xg, xh = lp.eng.alloc(8 * lp.n), lp.eng.alloc(8 * lp.n)
+    t0 = time.time()
+    ig, rg = sysm.bicgstab(lp.vec.ptr, xg.ptr, tol=1e-11, x0_is_zero=True)
+    t1 = time.time()
+    ih, rh = sysm.bicgstab(lp.vec.ptr, xh.ptr, tol=1e-11, x0_is_zero=True, graph=False)
+    t2 = time.time()
+    a, b = numpy.empty(lp.n), numpy.empty(lp.n)
+    xg.download(a), xh.download(b)
+    assert rg <= 1e-11 and rh <= 1e-11
+    assert abs(ig - ih) <= max(3, ih // 10)  # same algorithm, operations fused differently
+    assert numpy.abs(a - b).max() <= 1e-8 * numpy.abs(b).max()
+    print(f"graph: {ig} its {t1 - t0:.4f} s; host-driven: {ih} its {t2 - t1:.4f} s")
