@@ -34,6 +34,7 @@ def tuning(cell_dim=2):
         # resident CTAs per SM the register allocation must allow (__launch_bounds__)
         "min_ctas": int(os.environ.get("FVM_MIN_CTAS", "0")),
         "pair_loads": int(os.environ.get("FVM_PAIR_LOADS", "0")),
+        "row_runs": int(os.environ.get("FVM_ROW_RUNS", "0")),
     }
 
 # functor outputs per mode: (edge D, O, C), (vertex L, C), (dirichlet coeff, val)
@@ -194,6 +195,7 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         "FVM_EDGE_FACTORED": int(factored),
         "FVM_MIN_CTAS": tune["min_ctas"],
         "FVM_PAIR_LOADS": tune["pair_loads"],
+        "FVM_ROW_RUNS": tune["row_runs"],
         "FVM_EDGE_USES_X": int(edge_x),
         "FVM_EDGE_USES_U": int(edge_u),
         "FVM_VERT_USES_X": int(vert_x),

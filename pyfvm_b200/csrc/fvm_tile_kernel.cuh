@@ -64,6 +64,9 @@
 #define FVM_NCT (32 * FVM_CONSUMER_WARPS)  // consumer threads
 #define FVM_THREADS (FVM_NCT + 32)         // + one producer warp
 #define FVM_FULL 0xffffffffu
+#ifndef FVM_ROW_RUNS
+#define FVM_ROW_RUNS 0
+#endif
 #ifndef FVM_PAIR_LOADS
 #define FVM_PAIR_LOADS 0  // 1: 16-byte half-edge loads also on triangle meshes
 #endif
@@ -380,9 +383,13 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
     const FvmTileDesc* sd = (const FvmTileDesc*)(stage + L.desc);
     const int d_nr = sd->nr, d_s0 = sd->s0, d_nsl = sd->nsl, d_nhe = sd->nhe, d_r0 = sd->r0;
     const int v0 = a.row_base + d_r0;  // first vertex of the tile
-    // pass B: rows [ra, rb) of the tile belong to this warp
-    const int ra = (d_nr * cw) / FVM_CONSUMER_WARPS;
-    const int rb = (d_nr * (cw + 1)) / FVM_CONSUMER_WARPS;
+    // pass B: rows are dealt 32 at a time (lanes fill first: a 17-row tetrahedral tile
+    // keeps one warp busy instead of four warps with 4 lanes each); the warp that takes
+    // the first block rotates with the tile so the extra work spreads over the warps
+    const int rblock = (cw + it) % FVM_CONSUMER_WARPS;
+#if FVM_ROW_RUNS
+    const int ra = (d_nr * cw) / FVM_CONSUMER_WARPS, rb = (d_nr * (cw + 1)) / FVM_CONSUMER_WARPS;
+#endif
 
 #if FVM_MODE != FVM_MODE_SPMV
     const double* s_ce = (const double*)(stage + L.ce + fvm_shift_at(sd->h0, 8u));
@@ -553,7 +560,11 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
       asm volatile("bar.sync 1, %0;" ::"n"(FVM_NCT) : "memory");
 
       // ---------------- pass B: one lane per matrix row ------------------------
+#if FVM_ROW_RUNS  // (experiment: equal runs of rows per warp)
       for (int g = ra + lane; g < rb; g += 32) {
+#else
+      for (int g = rblock * 32 + lane; g < d_nr; g += FVM_NCT) {
+#endif
         const int b = s_rp[g] - d_s0, e = s_rp[g + 1] - d_s0;  // CSR slots of the row
         double sD = 0.0, sC = 0.0;
 #pragma unroll 1
