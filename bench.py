@@ -261,7 +261,7 @@ def run_ours(args):
             "seconds": cold_s,
             "value": R_global / cold_s,
             "unit": UNIT,
-            "what": "pyfvm.discretize_linear(problem, mesh) on an uncached mesh: sympy lowering, "
+            "what": "pyfvm.discretize_linear(problem, mesh) on an uncached mesh: sympy lowering (simplify memoised per expression), "
             "int64 index + geometry upload from pageable numpy arrays, on-device pattern build, "
             "assembly, indptr/indices/values/rhs back to the host",
         }

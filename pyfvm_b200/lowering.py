@@ -88,7 +88,21 @@ def lower_edge_integrand(integrand, u, dim):
     expr = expr.subs(sub, simultaneous=True)
     expr = CE * EL * expr
     expr = _flatten_dim(expr, dim)
-    return sympy.simplify(expr)
+    return _simplify_cached(expr)
+
+
+_SIMPLIFIED = {}
+
+
+def _simplify_cached(expr):
+    """``sympy.simplify`` dominates the lowering (~0.1 s per dS integrand); the same
+    problem is usually discretised many times (every mesh, every Newton restart),
+    so the result is memoised on the expression's structure."""
+    key = sympy.srepr(expr)
+    out = _SIMPLIFIED.get(key)
+    if out is None:
+        out = _SIMPLIFIED[key] = sympy.simplify(expr)
+    return out
 
 
 def _flatten_dim(expr, dim):
