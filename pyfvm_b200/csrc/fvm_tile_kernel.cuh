@@ -39,11 +39,15 @@
 //                    the CSR array (consecutive lanes -> consecutive slots:
 //                    coalesced) and parks the slot's diagonal / rhs share in
 //                    shared memory.  A named barrier over the math warps follows.
-//                    Pass B is ROW-parallel: the rows are dealt to the warps in
-//                    equal runs; lane l folds the parked shares of its row in slot
-//                    order, adds the vertex term, applies the Dirichlet row
-//                    replacement in the same pass and stores the diagonal value
-//                    and the rhs / residual entry.
+//                    Pass B is ROW-parallel: the rows are dealt to the warps 32 at a
+//                    time (the first warp rotates with the tile); lane l folds the
+//                    parked shares of its row in slot order, adds the vertex term,
+//                    applies the Dirichlet row replacement in the same pass and
+//                    stores the diagonal value and the rhs / residual entry.
+// Row-partitioned runs (fvm_assemble_halo): tiles are walked interior-first and the
+// producer acquires the neighbours' epoch flags (ld.acquire.sys) only before the u copies
+// of a tile whose vertex table reaches into ghost vertices -- the halo wait is part
+// of this kernel.
 // Deterministic and atomic-free: a slot is the in-order sum of its half-edges, a
 // row the in-order sum of its slots -- never a function of tile boundaries, the
 // warp count or the grid size, so a row-partitioned multi-GPU run is bit-identical
@@ -65,7 +69,7 @@
 #define FVM_THREADS (FVM_NCT + 32)         // + one producer warp
 #define FVM_FULL 0xffffffffu
 #ifndef FVM_ROW_RUNS
-#define FVM_ROW_RUNS 0
+#define FVM_ROW_RUNS 0  // 1: pass B rows in equal runs per warp (kept for A/B runs)
 #endif
 #ifndef FVM_PAIR_LOADS
 #define FVM_PAIR_LOADS 0  // 1: 16-byte half-edge loads also on triangle meshes
