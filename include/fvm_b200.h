@@ -73,6 +73,8 @@ int fvm_dev_free(fvm_ctx* ctx, void* ptr_dev);
 int fvm_dev_memset(fvm_ctx* ctx, void* ptr_dev, int value, size_t bytes);
 int fvm_h2d(fvm_ctx* ctx, void* dst_dev, const void* src, size_t bytes);
 int fvm_d2h(fvm_ctx* ctx, void* dst, const void* src_dev, size_t bytes);
+/* device -> device copy, stream-ordered on the ctx stream */
+int fvm_d2d(fvm_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
 /* device -> pinned host copy on the ctx's copy stream, ordered after the work issued
  * so far on the ctx stream; it overlaps whatever the ctx stream does next (e.g.
  * the next step's host -> device upload: PCIe is full duplex) */
@@ -136,9 +138,13 @@ int fvm_mesh_debug_copy(fvm_mesh* mesh, int which, void* out, size_t bytes);
 int fvm_mesh_get_pattern(fvm_mesh* mesh, int32_t* indptr, int32_t* indices);
 /* device views of the same arrays (owned by the mesh) */
 int fvm_mesh_pattern_dev(fvm_mesh* mesh, const int32_t** indptr_dev, const int32_t** indices_dev);
-/* re-upload per-record geometry (same connectivity), permuted on the device */
-int fvm_mesh_update_geometry(fvm_mesh* mesh, const double* ce_ratios, const double* edge_len,
-                             const double* coords, const double* control_volumes, int on_device);
+/* re-upload per-record geometry (same connectivity), permuted on the device.
+ * n_records / n_vertices are the lengths of the arrays handed in (ce_ratios, edge_len:
+ * n_records; coords: n_vertices*dim; control_volumes: n_vertices); the call fails when they
+ * differ from the mesh's.  Any of the four arrays may be NULL (left as is). */
+int fvm_mesh_update_geometry(fvm_mesh* mesh, int64_t n_records, int32_t n_vertices,
+                             const double* ce_ratios, const double* edge_len, const double* coords,
+                             const double* control_volumes, int on_device);
 
 /* ---- mesh generation and geometry on the device (the step before the
  * path).  meshplex derives idx_hierarchy / ce_ratios / ei_dot_ei / control_volumes

@@ -42,7 +42,8 @@ struct FvmTileDesc {  // 128 bytes, one per tile
   int nhalo;                 // halo ranges in use
   int hstart[FVM_NHALO];     // first vertex of every halo range (ascending, disjoint)
   unsigned short hcount[FVM_NHALO];
-  int pad[10];
+  int uncovered;             // != 0: some slot's column is outside the table (cold gather)
+  int pad[9];
 };
 
 #define FVM_META_LO_BITS 12

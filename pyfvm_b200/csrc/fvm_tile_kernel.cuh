@@ -266,7 +266,9 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
         tmin = min(tmin, sd->hstart[0]);
         tmax = max(tmax, sd->hstart[nhalo - 1] + (int)sd->hcount[nhalo - 1]);
       }
-      if (tmin < a.ghost_lo_end || tmax > a.ghost_hi_begin) {
+      // (a tile with columns outside its table gathers them from global memory: any of
+      // them may be a ghost vertex)
+      if (tmin < a.ghost_lo_end || tmax > a.ghost_hi_begin || d.uncovered) {
         fvm_halo_acquire(a);
         halo_ready = true;
       }
@@ -310,7 +312,9 @@ __device__ __noinline__ double4 fvm_gather_column(const int* colidx, const doubl
 #endif
 #endif
 #if FVM_EDGE_USES_U
-  r.w = __ldg(u + col);
+  // u may hold ghost values a peer GPU stored during this launch (ordered by the
+  // producer's flag acquire + the stage barrier): a coherent load, never ld.global.nc
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(r.w) : "l"(u + col) : "memory");
 #endif
   return r;
 }

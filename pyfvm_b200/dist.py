@@ -416,8 +416,16 @@ class DistributedFvm:
                 torch.from_numpy(u_owned).to(self.u_t.device)
             )
 
-    def exchange(self):
-        """Ghost values in place; returns the device address of the local ``u``."""
+    def exchange(self, mode=None):
+        """Ghost values in place; returns the device address of the local ``u``.
+        ``mode``: the launch this exchange feeds.  A launch that never reads ``u`` (the
+        Jacobian of a u-independent operator) gets no exchange at all: every epoch that
+        is pushed must also be waited for, or the double buffering of the peer halo
+        would let a fast rank overwrite values a slow rank still reads."""
+        if mode is not None and not self.s.functors[mode].needs_u:
+            if self.kind == "peer":
+                return self.halo.u_ptr(self.halo.next_buffer())
+            return self.u_t.data_ptr()
         if self.kind == "peer":
             return self.halo.exchange(wait=not self.fused)
         import torch
@@ -443,7 +451,7 @@ class DistributedFvm:
     def eval(self, u_owned):
         """Owned rows of ``f.eval(u)`` [README:121]."""
         self.set_owned(u_owned)
-        self.residual_device(self.exchange())
+        self.residual_device(self.exchange(codegen.MODE_RESIDUAL))
         out = numpy.empty(self.part.n_owned)
         self.F.download(out)
         if self.kind == "peer":
@@ -456,9 +464,11 @@ class DistributedFvm:
         from scipy import sparse
 
         self.set_owned(u_owned)
-        self.jacobian_device(self.exchange())
+        self.jacobian_device(self.exchange(codegen.MODE_JACOBIAN))
         data = numpy.empty(self.s.nnz)
         self.s.data.download(data)
+        if self.kind == "peer":
+            self.halo.check_timeout()
         indptr, indices = self.s.dmesh.pattern()
         return sparse.csr_matrix(
             (data, self.part.verts[indices].astype(numpy.int32), indptr),

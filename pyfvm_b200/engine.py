@@ -70,6 +70,7 @@ SYMBOLS = {
     "fvm_dev_memset": (c_int, [c_void_p, c_void_p, c_int, c_size_t]),
     "fvm_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "fvm_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "fvm_d2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "fvm_d2h_async": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "fvm_copy_fence": (c_int, [c_void_p]),
     "fvm_copy_sync": (c_int, [c_void_p]),
@@ -87,7 +88,9 @@ SYMBOLS = {
     "fvm_mesh_debug_copy": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     "fvm_mesh_get_pattern": (c_int, [c_void_p, c_void_p, c_void_p]),
     "fvm_mesh_pattern_dev": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
-    "fvm_mesh_update_geometry": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "fvm_mesh_update_geometry": (
+        c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int],
+    ),
     "fvm_gen_rectangle_tri": (
         c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     ),
@@ -256,9 +259,11 @@ class Engine:
     def alloc(self, nbytes):
         return DeviceBuffer(self, nbytes)
 
-    def to_device(self, arr):
+    def to_device(self, arr, pad=0):
+        """Upload ``arr``; ``pad`` spare bytes after it (the tile kernel's bulk copies are
+        rounded up to 16 bytes and may read that far past the last element)."""
         arr = numpy.ascontiguousarray(arr)
-        return self.alloc(arr.nbytes).upload(arr)
+        return self.alloc(arr.nbytes + pad).upload(arr)
 
     def pinned_empty(self, shape, dtype):
         """numpy array in page-locked host memory (fast, async-capable copies)."""
@@ -441,11 +446,13 @@ class DeviceMesh:
             ms.value,
         )
         self._pattern = None
+        self.shared = False  # True while other problems may hold this object (mesh cache)
 
     TILE_DTYPE = numpy.dtype(
         [("h0", "<i8"), ("r0", "<i4"), ("nr", "<i4"), ("s0", "<i4"), ("nsl", "<i4"),
          ("nhe", "<i4"), ("own_start", "<i4"), ("own_count", "<i4"), ("nhalo", "<i4"),
-         ("hstart", "<i4", (8,)), ("hcount", "<u2", (8,)), ("pad", "<i4", (10,))]
+         ("hstart", "<i4", (8,)), ("hcount", "<u2", (8,)), ("uncovered", "<i4"),
+         ("pad", "<i4", (9,))]
     )
 
     def stats(self):
@@ -500,8 +507,13 @@ class DeviceMesh:
         (host arrays; the device permutes records into half-edge order)."""
         arrs = [None if a is None else numpy.ascontiguousarray(a, dtype=numpy.float64)
                 for a in (ce, el, coords, cv)]
+        for a, want in zip(arrs, (self.R, self.R, self.n * self.dim, self.n)):
+            if a is not None and a.size != want:
+                raise ValueError(f"update_geometry: array of {a.size} entries, expected {want}")
         self.eng._ck(
-            self.eng.lib.fvm_mesh_update_geometry(self.handle, *[_ptr(a) for a in arrs], 0)
+            self.eng.lib.fvm_mesh_update_geometry(
+                self.handle, self.R, self.n, *[_ptr(a) for a in arrs], 0
+            )
         )
 
     def launch(self, kernel, vmask=None, dirid=None, u=None, data=None, vec=None, halo=None):
@@ -525,19 +537,57 @@ class DeviceMesh:
 _mesh_cache = {}
 
 
-def device_mesh(eng, mesh, rec_mask=None, need_el=False, row_range=None):
-    """Cached :class:`DeviceMesh` of ``mesh`` (key: mesh identity, subdomain bits,
-    owned row range)."""
+def _array_sig(a):
+    """Identity + a sampled content hash of one mesh array (cheap: <= 4096 samples)."""
+    a = numpy.asarray(a)
+    flat = a.reshape(-1) if a.flags["C_CONTIGUOUS"] else a.ravel()
+    step = max(1, flat.size // 4096)
+    sample = numpy.ascontiguousarray(flat[::step])
+    return (
+        a.__array_interface__["data"][0], a.shape, a.dtype.str,
+        hashlib.blake2b(sample.tobytes(), digest_size=8).hexdigest(),
+    )
+
+
+def mesh_fingerprint(mesh):
+    """What a cached :class:`DeviceMesh` was built from.  meshplex meshes are mutable
+    (points moved, edges flipped: its derived arrays are then NEW array objects), and the
+    reference re-reads the mesh on every call; a cached device mesh is only reused while
+    the arrays it mirrors are the same objects with the same (sampled) content."""
+    coords = mesh.node_coords if hasattr(mesh, "node_coords") else mesh.points
+    sig = [_array_sig(coords)]
+    if hasattr(mesh, "device_records"):
+        sig.append(("device", id(getattr(mesh, "_cells", None)), getattr(mesh, "n_records", 0)))
+    else:
+        sig += [_array_sig(mesh.idx_hierarchy), _array_sig(mesh.ce_ratios),
+                _array_sig(mesh.control_volumes)]
+    return tuple(sig)
+
+
+def device_mesh(eng, mesh, rec_mask=None, need_el=False, row_range=None, cache=True):
+    """:class:`DeviceMesh` of ``mesh``, cached per mesh object (key: mesh identity,
+    subdomain bits, owned row range) and revalidated against ``mesh_fingerprint`` on
+    every hit.  Mesh objects that cannot be weak-referenced are never cached (their
+    ``id`` could be reused by another mesh)."""
     mkey = None if rec_mask is None else hashlib.sha256(rec_mask.tobytes()).hexdigest()
     key = (id(mesh), eng.device, mkey, row_range)
-    dm = _mesh_cache.get(key)
-    if dm is not None and need_el and not dm.has_el:
-        dm = None  # rebuild with the edge-length stream
-    if dm is None:
-        dm = DeviceMesh(eng, mesh, rec_mask=rec_mask, need_el=need_el, row_range=row_range)
-        _mesh_cache[key] = dm
+    fp = None
+    if cache:
         try:
-            weakref.finalize(mesh, _mesh_cache.pop, key, None)
+            weakref.ref(mesh)
+            fp = mesh_fingerprint(mesh)
         except TypeError:
-            pass  # mesh object not weak-referenceable: cache lives with the process
+            cache = False
+    hit = _mesh_cache.get(key) if cache else None
+    if hit is not None and (hit[0] != fp or (need_el and not hit[1].has_el)):
+        _mesh_cache.pop(key, None)  # stale geometry / connectivity, or no edge lengths
+        hit[1].shared = False
+        hit = None
+    if hit is not None:
+        return hit[1]
+    dm = DeviceMesh(eng, mesh, rec_mask=rec_mask, need_el=need_el, row_range=row_range)
+    dm.shared = bool(cache)
+    if cache:
+        _mesh_cache[key] = (fp, dm)
+        weakref.finalize(mesh, _mesh_cache.pop, key, None)
     return dm

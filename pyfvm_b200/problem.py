@@ -98,12 +98,14 @@ class _DeviceProblem:
         )
         self.n_rows = self.dmesh.n_rows
         self.kernels = {m: eng.kernel(f, fmad=fmad) for m, f in self.functors.items()}
-        self.vmask = eng.to_device(vmask) if vmask is not None else None
-        self.dirid = eng.to_device(dirid) if dirid is not None else None
+        # (+16: the kernel's 16-byte-rounded bulk copies may read past the last element)
+        self.vmask = eng.to_device(vmask, pad=16) if vmask is not None else None
+        self.dirid = eng.to_device(dirid, pad=16) if dirid is not None else None
         self.nnz = self.dmesh.nnz
-        self.data = eng.alloc(8 * self.nnz)
-        self.vec = eng.alloc(8 * n)
-        self.u = eng.alloc(8 * n)
+        self.data = eng.alloc(8 * self.nnz + 16)
+        self.vec = eng.alloc(8 * n + 16)
+        self.u = eng.alloc(8 * n + 16)
+        self._mesh_args = (mesh, rec_mask, need_el, row_range)
 
     def _p(self, buf):
         return None if buf is None else buf.ptr
@@ -138,6 +140,14 @@ class _DeviceProblem:
             self._tpat = (torch.from_numpy(indptr).to(device), torch.from_numpy(indices).to(device))
         return self._tpat
 
+    def padded_u(self, ptr):
+        """A caller's device array of an ODD number of doubles has no slack for the
+        kernel's even-count bulk copies: it goes through the padded internal buffer."""
+        if self.n % 2 == 0:
+            return ptr
+        self.eng._ck(self.eng.lib.fvm_d2d(self.eng.ctx, self.u.ptr, ptr, 8 * self.n))
+        return self.u.ptr
+
     def upload_u(self, u):
         u = numpy.ascontiguousarray(u, dtype=numpy.float64)
         assert u.shape == (self.n,), "u must have one value per vertex"
@@ -153,6 +163,17 @@ class LinearProblem(_DeviceProblem):
         super().__init__(obj, mesh, "linear", **kw)
 
     def update_geometry(self, **kw):
+        """Re-upload geometry of the same connectivity.  The cached device mesh is shared
+        by every problem built on that mesh object, so the first update moves this
+        problem onto a private copy (one more pattern build) instead of changing the
+        geometry under the others."""
+        if self.dmesh.shared:
+            from .engine import DeviceMesh
+
+            mesh, rec_mask, need_el, row_range = self._mesh_args
+            self.dmesh = DeviceMesh(
+                self.eng, mesh, rec_mask=rec_mask, need_el=need_el, row_range=row_range
+            )
         self.dmesh.update_geometry(**kw)
 
     def assemble_device(self):
@@ -236,7 +257,7 @@ class FvmProblem:
             assert n == s.n and ptr % 16 == 0, "u must hold one 16-byte aligned double per vertex"
             _sync_producer(u)
             out = _device_like(u, s.n_rows)
-            self.eval_device(ptr, out.data_ptr())
+            self.eval_device(s.padded_u(ptr), out.data_ptr())
             s.eng.sync()
             return out
         self.eval_device(s.upload_u(u))
@@ -279,7 +300,7 @@ class Jacobian:
         assert n == s.n and ptr % 16 == 0
         _sync_producer(u)
         values = torch.empty(s.nnz, dtype=torch.float64, device=u.device)
-        self.values_device(ptr, values.data_ptr())
+        self.values_device(s.padded_u(ptr), values.data_ptr())
         s.eng.sync()
         crow, col = s.torch_pattern(u.device)
         return torch.sparse_csr_tensor(crow, col, values, size=(s.n_rows, s.n))

@@ -294,6 +294,8 @@ def newton_distributed(dp, u0_owned, tol=1e-10, max_iter=20, lin_tol=1e-10, verb
             dp.jacobian_device(u_ptr)
             its, _ = sysm.bicgstab(dp.F.ptr, du.ptr, tol=lin_tol, x0_is_zero=True)
             lin_its += its
+            dp.halo.check_timeout()  # a halo wait that gave up must not feed the next step
+            sysm.vhalo.check_timeout()
             nxt = dp.halo.u_ptr(dp.halo.next_buffer()) + off
             sysm._axpby(1.0, u_ptr + off, -1.0, du.ptr, nxt)  # u_new = u - du, owned part
             u_ptr = dp.exchange()

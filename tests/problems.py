@@ -136,3 +136,21 @@ def cube(n):
 
     xs = numpy.linspace(0.0, 1.0, n)
     return meshes.cube_tetra(xs, xs, xs)
+
+
+def shuffle_numbering(points, cells, seed=0, window=None):
+    """The same mesh with its vertices renumbered: a random permutation of all
+    vertices (``window=None``) or of blocks of ``window`` consecutive vertices.
+    Real meshio / gmsh meshes [README:56-64] have no lexicographic numbering; this is
+    what makes a tile's columns fall outside its staged vertex table."""
+    n = len(points)
+    rng = numpy.random.default_rng(seed)
+    if window is None:
+        old_of_new = rng.permutation(n)
+    else:
+        old_of_new = numpy.concatenate(
+            [lo + rng.permutation(min(window, n - lo)) for lo in range(0, n, window)]
+        )
+    new_of_old = numpy.empty(n, dtype=numpy.int64)
+    new_of_old[old_of_new] = numpy.arange(n)
+    return numpy.ascontiguousarray(points[old_of_new]), new_of_old[cells]

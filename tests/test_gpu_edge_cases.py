@@ -185,3 +185,81 @@ def test_device_resident_handoff_torch():
     assert bt.cpu().numpy().tobytes() == b.tobytes()
     x = torch.from_numpy(u).cuda()
     assert numpy.allclose((At @ x).cpu().numpy(), A @ u, rtol=1e-12, atol=1e-12)
+
+
+def _moved(mesh, p2):
+    """Move a mesh's points the way meshplex does: derived arrays are recomputed (new
+    array objects), the mesh object stays the same."""
+    mesh.points = p2
+    nc = numpy.zeros((len(p2), 3))
+    nc[:, : p2.shape[1]] = p2
+    mesh.node_coords = nc
+    mesh._geom = mesh._cv = None
+
+
+def test_mesh_cache_revalidates_a_mutated_mesh():
+    """A second discretize on the SAME mesh object after its points moved must see the
+    new geometry (the reference re-reads the mesh on every call)."""
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import meshes
+
+    p, c = problems.rectangle(31, 19)
+    mesh = meshes.Mesh(p, c)
+    P = problems.convection_diffusion(eng.form_language)
+    A0, b0 = eng.discretize_linear(P, mesh)
+    p2, _ = meshes.jitter(p, c, scale=0.1, seed=5)
+    _moved(mesh, p2)
+    A1, b1 = eng.discretize_linear(P, mesh)
+    A2, b2 = eng.discretize_linear(P, meshes.Mesh(p2, c))
+    assert A1.data.tobytes() == A2.data.tobytes() and b1.tobytes() == b2.tobytes()
+    assert A1.data.tobytes() != A0.data.tobytes()
+
+
+def test_update_geometry_is_private_to_its_problem():
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import meshes, problem
+
+    p, c = problems.rectangle(23, 15)
+    mesh = meshes.Mesh(p, c)
+    P = problems.convection_diffusion(eng.form_language)
+    lp_a = problem.LinearProblem(P, mesh)
+    lp_b = problem.LinearProblem(P, mesh)
+    assert lp_a.dmesh is lp_b.dmesh  # shared through the mesh cache
+    A0, _ = lp_b.assemble()
+    moved = meshes.Mesh(meshes.jitter(p, c, scale=0.1, seed=6)[0], c)
+    lp_a.update_geometry(ce=numpy.asarray(moved.ce_ratios).reshape(-1), coords=moved.points,
+                         cv=moved.control_volumes)
+    assert lp_a.dmesh is not lp_b.dmesh
+    A1, _ = lp_b.assemble()
+    assert A1.data.tobytes() == A0.data.tobytes()
+    with pytest.raises(ValueError):
+        lp_a.update_geometry(ce=numpy.zeros(7))
+
+
+def test_out_of_range_endpoint_is_refused():
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import engine, meshes
+
+    mesh = meshes.Mesh(*problems.rectangle(9, 7))
+    idx = numpy.array(mesh.idx_hierarchy)
+    idx[1, 0, 3] = len(mesh.points) + 5
+    mesh._idx = idx
+    with pytest.raises(engine.FvmError, match="outside"):
+        eng.discretize_linear(problems.poisson(eng.form_language), mesh)
+
+
+def test_odd_length_device_u():
+    """f.eval on a torch tensor with an odd number of vertices (no slack after the last
+    element) goes through the padded internal buffer."""
+    import torch
+
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import meshes
+
+    mesh = meshes.Mesh(*problems.rectangle(21, 13))  # 273 vertices
+    assert len(mesh.points) % 2 == 1
+    f, jac = eng.discretize(problems.bratu(eng.form_language), mesh)
+    u = 0.2 * numpy.random.default_rng(0).standard_normal(len(mesh.points))
+    F_host = f.eval(u)
+    F_dev = f.eval(torch.from_numpy(u).cuda())
+    assert F_dev.cpu().numpy().tobytes() == F_host.tobytes()

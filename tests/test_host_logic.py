@@ -149,3 +149,23 @@ def test_vtk_output(tmp_path):
     mesh.write(str(out), point_data={"x": x})
     text = out.read_text()
     assert "POINTS 20 double" in text and "CELLS 24 96" in text and "SCALARS x double 1" in text
+
+
+def test_mesh_fingerprint_tracks_mutation():
+    """The device-mesh cache key (no GPU needed): same object + same arrays -> same
+    fingerprint; moved points or flipped cells -> different."""
+    from pyfvm_b200 import engine, meshes
+    from tests import problems
+
+    p, c = problems.rectangle(17, 11)
+    mesh = meshes.Mesh(p, c)
+    fp0 = engine.mesh_fingerprint(mesh)
+    assert engine.mesh_fingerprint(mesh) == fp0
+    p2 = p.copy()
+    p2[40] += 1e-3
+    mesh.points = p2
+    mesh.node_coords = numpy.concatenate([p2, numpy.zeros((len(p2), 1))], axis=1)
+    mesh._geom = mesh._cv = None
+    assert engine.mesh_fingerprint(mesh) != fp0
+    other = meshes.Mesh(p, c[::-1].copy())
+    assert engine.mesh_fingerprint(other) != fp0
