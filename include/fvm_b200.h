@@ -128,7 +128,8 @@ int fvm_mesh_info(fvm_mesh* mesh, int64_t* nnz, int64_t* n_halfedges, int32_t* n
                   float* build_ms);
 /* layout diagnostics, out[0..n): largest tile (half-edges, slots, rows, vertex-table
  * entries), slots whose column lies outside the staged vertex tables (they are
- * gathered from global memory instead), tile quantum, tiles, half-edges */
+ * gathered from global memory instead), tile quantum, tiles, half-edges, length of the
+ * padded half-edge streams (every slot starts even and holds an even number of entries) */
 int fvm_mesh_stats(fvm_mesh* mesh, int64_t* out, int n);
 /* copy an internal layout array to the host for inspection / tests:
  * 0 = tile descriptors (128 B each), 1 = packed slot metadata (4 B per slot),

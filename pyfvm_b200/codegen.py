@@ -33,8 +33,16 @@ def tuning(cell_dim=2):
         "factor_ce": int(os.environ.get("FVM_FACTOR_CE", "1")),
         # resident CTAs per SM the register allocation must allow (__launch_bounds__)
         "min_ctas": int(os.environ.get("FVM_MIN_CTAS", "0")),
-        "pair_loads": int(os.environ.get("FVM_PAIR_LOADS", "0")),
-        "row_runs": int(os.environ.get("FVM_ROW_RUNS", "0")),
+        # multi-pair slots: pairs loaded before the in-order adds start (-1: template default)
+        "fold_ahead": int(os.environ.get("FVM_FOLD_AHEAD", "-1")),
+        # row pass: equal runs of rows per warp (triangles: ~104 rows per tile, 26 per warp)
+        # or 32-row blocks dealt to the warps (tetrahedra: ~17 rows per tile, one warp)
+        # slot pass: 32-slot chunks a warp keeps in flight together; row pass: shares loaded
+        # ahead of the in-order adds (-1: template defaults)
+        "ilp": int(os.environ.get("FVM_ILP", "-1")),
+        "row_ahead": int(os.environ.get("FVM_ROW_AHEAD", "-1")),
+        # (2: decided per tile by its row count -- the template's default)
+        "row_runs": int(os.environ.get("FVM_ROW_RUNS", "2")),
     }
 
 # functor outputs per mode: (edge D, O, C), (vertex L, C), (dirichlet coeff, val)
@@ -194,7 +202,6 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         "FVM_STAGES": tune["stages"],
         "FVM_EDGE_FACTORED": int(factored),
         "FVM_MIN_CTAS": tune["min_ctas"],
-        "FVM_PAIR_LOADS": tune["pair_loads"],
         "FVM_ROW_RUNS": tune["row_runs"],
         "FVM_EDGE_USES_X": int(edge_x),
         "FVM_EDGE_USES_U": int(edge_u),
@@ -208,6 +215,9 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
     if bad:
         raise ValueError(f"undefined functions cannot be lowered to device code: {sorted(bad)}")
 
+    for key, macro in (("fold_ahead", "FVM_FOLD_AHEAD"), ("ilp", "FVM_ILP"), ("row_ahead", "FVM_ROW_AHEAD")):
+        if tune.get(key, -1) >= 0:
+            defs[macro] = tune[key]
     L = [f"// generated by pyfvm_b200.codegen (mode {mode}); do not edit"]
     L += [f"#define {k} {v}" for k, v in defs.items()]
     L.append("")

@@ -22,10 +22,16 @@
 // global load.  Ranges start at even vertices and have even length: every bulk
 // copy is 16-byte aligned for 8-byte elements.
 //
+// The half-edge streams are PADDED: every slot starts at an even position and holds an
+// even number of entries (an odd slot gets one entry with ce = +0.0, mask 0), so a slot's
+// ce_ratios are read with aligned 16-byte loads ("pairs") only.
+//
 // slot_meta has one entry per OFF-DIAGONAL CSR slot (the diagonal slot of a row owns
 // no half-edge; the row pass writes it), packing everything the slot-parallel pass
 // needs:
-//   bits  0..11  first half-edge of the slot, relative to the tile   (< 4096)
+//   bits  0..10  first pair (16-byte unit) of the slot, relative to the tile  (< 2048)
+//   bit  11      the slot holds more than one pair (then the next entry's pair index,
+//                or the tile's end, closes it; interior triangle-mesh slots hold one)
 //   bits 12..19  row of the slot, relative to the tile               (< 256)
 //   bit  20      the slot sits after its row's diagonal slot
 //   bits 21..31  index of the slot's column in the tile's vertex table
@@ -46,9 +52,9 @@ struct FvmTileDesc {  // 128 bytes, one per tile
   int pad[9];
 };
 
-#define FVM_META_LO_BITS 12
-#define FVM_META_ROW_BITS 8
-#define FVM_META_LO_MASK 0xfffu
+#define FVM_META_PAIR_MASK 0x7ffu
+#define FVM_META_MULTI_BIT 11
+#define FVM_META_ROW_SHIFT 12
 #define FVM_META_ROW_MASK 0xffu
 #define FVM_META_AFTER_BIT 20
 #define FVM_META_XL_SHIFT 21

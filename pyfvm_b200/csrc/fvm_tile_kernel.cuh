@@ -69,10 +69,21 @@
 #define FVM_THREADS (FVM_NCT + 32)         // + one producer warp
 #define FVM_FULL 0xffffffffu
 #ifndef FVM_ROW_RUNS
-#define FVM_ROW_RUNS 0  // 1: pass B rows in equal runs per warp (kept for A/B runs)
+// pass B row dealing: 0 = 32-row blocks round-robin over the warps, 1 = equal runs of rows
+// per warp, 2 = decided per tile (runs when the tile has >= 64 rows: ~104-row triangle
+// tiles give every warp 26 rows; ~17-row tetrahedral tiles keep one warp's lanes busy)
+#define FVM_ROW_RUNS 2
 #endif
-#ifndef FVM_PAIR_LOADS
-#define FVM_PAIR_LOADS 0  // 1: 16-byte half-edge loads also on triangle meshes
+#ifndef FVM_ILP
+#define FVM_ILP 2  // 32-slot chunks a warp keeps in flight together in the slot pass
+#endif
+#ifndef FVM_ROW_AHEAD
+#define FVM_ROW_AHEAD 6  // parked shares of a row loaded before the in-order adds start
+#endif
+#ifndef FVM_FOLD_AHEAD
+// pairs of a multi-pair slot whose loads are issued before the in-order adds start
+// (tetrahedra: 4 or 6 pairs per slot; the loads are independent, the adds are not)
+#define FVM_FOLD_AHEAD 0  // (measured on 200^3: 0 beats 3 and 5 -- the selects cost more)
 #endif
 
 static_assert(!(FVM_EDGE_USES_X || FVM_VERT_USES_X) || FVM_STAGE_X, "FVM_F_X missing");
@@ -391,17 +402,19 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
     const FvmTileDesc* sd = (const FvmTileDesc*)(stage + L.desc);
     const int d_nr = sd->nr, d_s0 = sd->s0, d_nsl = sd->nsl, d_nhe = sd->nhe, d_r0 = sd->r0;
     const int v0 = a.row_base + d_r0;  // first vertex of the tile
-    // pass B: rows are dealt 32 at a time (lanes fill first: a 17-row tetrahedral tile
-    // keeps one warp busy instead of four warps with 4 lanes each); the warp that takes
-    // the first block rotates with the tile so the extra work spreads over the warps
-    const int rblock = (cw + it) % FVM_CONSUMER_WARPS;
-#if FVM_ROW_RUNS
-    const int ra = (d_nr * cw) / FVM_CONSUMER_WARPS, rb = (d_nr * (cw + 1)) / FVM_CONSUMER_WARPS;
-#endif
+    // pass B row dealing (FVM_ROW_RUNS): blocks of 32 rows (lanes fill first: a 17-row
+    // tetrahedral tile keeps one warp busy instead of four warps with 4 lanes each; the warp
+    // that takes the first block rotates with the tile) or equal runs of rows per warp
+    int g_first = ((cw + it) % FVM_CONSUMER_WARPS) * 32, g_end = d_nr, g_step = FVM_NCT;
+    if (FVM_ROW_RUNS == 1 || (FVM_ROW_RUNS == 2 && d_nr >= 64)) {
+      g_first = (d_nr * cw) / FVM_CONSUMER_WARPS;
+      g_end = (d_nr * (cw + 1)) / FVM_CONSUMER_WARPS;
+      g_step = 32;
+    }
 
 #if FVM_MODE != FVM_MODE_SPMV
-    const double* s_ce = (const double*)(stage + L.ce + fvm_shift_at(sd->h0, 8u));
-    const int ce_odd = (int)(fvm_shift_at(sd->h0, 8u) >> 3);  // 1: s_ce[0] sits at 8 mod 16
+    // a tile starts at a slot start: even position of the padded stream, 16-byte aligned
+    const double2* s_ce2 = (const double2*)(stage + L.ce);
 #else
     const double* s_mat = (const double*)(stage + L.mat + fvm_shift_at(d_s0, 8u));
 #endif
@@ -411,7 +424,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
     const int xoff = v0 - sd->own_start;  // table index of the tile's first row
     const int* s_rp = (const int*)(stage + L.rowptr + fvm_shift_at(d_r0, 4u));
 #if FVM_EDGE_USES_EL
-    const double* s_el = (const double*)(stage + L.el + fvm_shift_at(sd->h0, 8u));
+    const double* s_el = (const double*)(stage + L.el);
 #endif
 #if FVM_EDGE_MASKED
     const unsigned char* s_mask = stage + L.mask + fvm_shift_at(sd->h0, 1u);
@@ -444,139 +457,204 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
 
     {
       // ---------------- pass A: one lane per off-diagonal CSR slot -------------
-      // 32-slot chunks dealt round-robin to the math warps
+      // 32-slot chunks; a warp takes FVM_ILP consecutive chunks per trip and keeps their
+      // (independent) load -> functor chains in flight together: with 4 math warps per
+      // scheduler the pass is bound by the latency of one chain, not by issue slots.
+      // Lanes past the tile's last slot run on entry 0 of the tile (valid addresses) and
+      // store nothing.
 #pragma unroll 1
-      for (int k = cw * 32 + lane; k < d_nk; k += FVM_NCT) {
-        const unsigned meta = s_meta[k];
-#if FVM_MODE != FVM_MODE_SPMV
-        const int lo = (int)(meta & FVM_META_LO_MASK);
-        const int hi = (k + 1 < d_nk) ? (int)(s_meta[k + 1] & FVM_META_LO_MASK) : d_nhe;
-#endif
-        const int g = (int)((meta >> FVM_META_LO_BITS) & FVM_META_ROW_MASK);  // row of the slot
-        // CSR slot (tile-relative): one diagonal slot per earlier row, plus this row's
-        const int s = k + g + (int)((meta >> FVM_META_AFTER_BIT) & 1u);
-        double aD = 0.0, aO = 0.0, aC = 0.0;
-        double x00 = 0.0, x01 = 0.0, x02 = 0.0, u0 = 0.0;
-        double x10 = 0.0, x11 = 0.0, x12 = 0.0, u1 = 0.0;
-#if FVM_EDGE_USES_X
-        {
-          const double2 q0 = *(const double2*)(s_xy + FVM_XS * (xoff + g));
-          x00 = q0.x;
-          x01 = q0.y;
-#if FVM_DIM == 3
-          x02 = s_xy[FVM_XS * (xoff + g) + 2];
-#endif
+      for (int kb = cw * (32 * FVM_ILP) + lane; kb < d_nk + lane; kb += FVM_NCT * FVM_ILP) {
+        unsigned meta[FVM_ILP];
+        int kk[FVM_ILP];
+        bool act[FVM_ILP];
+#pragma unroll
+        for (int j = 0; j < FVM_ILP; ++j) {
+          kk[j] = kb + 32 * j;
+          act[j] = kk[j] < d_nk;
+          meta[j] = s_meta[act[j] ? kk[j] : 0];
         }
+        int g[FVM_ILP], sl[FVM_ILP];
+        double x00[FVM_ILP], x01[FVM_ILP], x02[FVM_ILP], u0[FVM_ILP];
+        double x10[FVM_ILP], x11[FVM_ILP], x12[FVM_ILP], u1[FVM_ILP];
+        double ce[FVM_ILP];
+#if FVM_MODE != FVM_MODE_SPMV
+        int lo2[FVM_ILP], n2[FVM_ILP];
+#endif
+        // ---- loads of all chains first
+#pragma unroll
+        for (int j = 0; j < FVM_ILP; ++j) {
+          const unsigned m = meta[j];
+          g[j] = (int)((m >> FVM_META_ROW_SHIFT) & FVM_META_ROW_MASK);  // row of the slot
+          // CSR slot (tile-relative): one diagonal slot per earlier row, plus this row's
+          sl[j] = kk[j] + g[j] + (int)((m >> FVM_META_AFTER_BIT) & 1u);
+          x00[j] = x01[j] = x02[j] = u0[j] = 0.0;
+          x10[j] = x11[j] = x12[j] = u1[j] = 0.0;
+          ce[j] = 0.0;
+#if FVM_MODE != FVM_MODE_SPMV
+          lo2[j] = (int)(m & FVM_META_PAIR_MASK);  // first pair of the slot
+          n2[j] = 1;                               // pairs of the slot
+          if ((m >> FVM_META_MULTI_BIT) & 1u)
+            n2[j] = ((kk[j] + 1 < d_nk) ? (int)(s_meta[kk[j] + 1] & FVM_META_PAIR_MASK)
+                                        : (d_nhe >> 1)) - lo2[j];
+#if FVM_EDGE_FACTORED
+          {
+            const double2 p = s_ce2[lo2[j]];
+            ce[j] = p.x + p.y;  // (the first pair of the fold; padding entries are +0.0)
+          }
+#endif
+#endif
+#if FVM_EDGE_USES_X
+          {
+            const double2 q0 = *(const double2*)(s_xy + FVM_XS * (xoff + g[j]));
+            x00[j] = q0.x;
+            x01[j] = q0.y;
+#if FVM_DIM == 3
+            x02[j] = s_xy[FVM_XS * (xoff + g[j]) + 2];
+#endif
+          }
 #endif
 #if FVM_EDGE_USES_U
-        u0 = s_u[xoff + g];
+          u0[j] = s_u[xoff + g[j]];
 #endif
 #if FVM_EDGE_USES_X || FVM_EDGE_USES_U
-        const unsigned xl = meta >> FVM_META_XL_SHIFT;
-        if (xl != FVM_XLOC_NONE) {
+          const unsigned xl = m >> FVM_META_XL_SHIFT;
+          if (xl != FVM_XLOC_NONE) {
 #if FVM_EDGE_USES_X
-          const double2 q = *(const double2*)(s_xy + FVM_XS * xl);
-          x10 = q.x;
-          x11 = q.y;
+            const double2 q = *(const double2*)(s_xy + FVM_XS * xl);
+            x10[j] = q.x;
+            x11[j] = q.y;
 #if FVM_DIM == 3
-          x12 = s_xy[FVM_XS * xl + 2];
+            x12[j] = s_xy[FVM_XS * xl + 2];
 #endif
 #endif
 #if FVM_EDGE_USES_U
-          u1 = s_u[xl];
+            u1[j] = s_u[xl];
 #endif
-        } else {  // column outside the staged halo ranges: gather it (cold path)
-          const double4 gq = fvm_gather_column(a.colidx, a.coords, a.u, d_s0 + s);
-          x10 = gq.x;
-          x11 = gq.y;
-          x12 = gq.z;
-          u1 = gq.w;
-        }
-#endif
-#if FVM_MODE == FVM_MODE_SPMV
-        aC = s_mat[s] * u1;
-#elif FVM_EDGE_FACTORED
-        // every edge term is ce * g(slot): fold the ce_ratios, evaluate g once
-#if FVM_DIM == 3 || FVM_PAIR_LOADS
-        // tetrahedra: ~10 half-edges per slot; after an odd head element the slot's
-        // half-edges are read two at a time with 16-byte loads
-        double ce;
-        int kk = lo;
-        if (((lo ^ ce_odd) & 1) == 0 && hi - lo > 1) {
-          const double2 p = *(const double2*)(s_ce + lo);
-          ce = p.x + p.y;
-          kk = lo + 2;
-        } else {
-          ce = s_ce[lo];
-          kk = lo + 1;
-        }
-#pragma unroll 1
-        for (; kk + 1 < hi; kk += 2) {  // kk is 16-byte aligned from here on
-          // 16-byte loads: lanes a stride of ~10 half-edges apart hit distinct banks
-          const double2 p = *(const double2*)(s_ce + kk);
-          ce += p.x;  // still in half-edge order
-          ce += p.y;
-        }
-        if (kk < hi) ce += s_ce[kk];
-#else
-        // triangles: two half-edges per interior slot
-        double ce = s_ce[lo];
-        if (hi - lo > 1) {
-          ce += s_ce[lo + 1];
-          if (hi - lo > 2) {
-#pragma unroll 1
-            for (int kk = lo + 2; kk < hi; ++kk) ce += s_ce[kk];
+          } else {  // column outside the staged halo ranges: gather it (cold path)
+            const double4 gq = fvm_gather_column(a.colidx, a.coords, a.u, d_s0 + sl[j]);
+            x10[j] = gq.x;
+            x11[j] = gq.y;
+            x12[j] = gq.z;
+            u1[j] = gq.w;
           }
-        }
 #endif
-        fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, 0.0, 0xffu, aD, aO, aC);
-#else
-        // the edge functor is evaluated per half-edge (edge_length / subdomain bits
-        // vary inside a slot)
+        }
+        // ---- functor + stores
+#pragma unroll
+        for (int j = 0; j < FVM_ILP; ++j) {
+          double aD = 0.0, aO = 0.0, aC = 0.0;
+#if FVM_MODE == FVM_MODE_SPMV
+          aC = s_mat[sl[j]] * u1[j];
+#elif FVM_EDGE_FACTORED
+          // every edge term is ce * g(slot): fold the slot's ce_ratios in half-edge order
+          // (aligned 16-byte loads), evaluate g once
+          if (n2[j] > 1) {  // triangles: irregular slots only; tetrahedra: always (4 or 6)
+            const double2* cp = s_ce2 + lo2[j];
+            int i = 1;
+#if FVM_FOLD_AHEAD > 1
+            {
+              double2 q[FVM_FOLD_AHEAD];
+#pragma unroll
+              for (int t = 0; t < FVM_FOLD_AHEAD; ++t)
+                if (1 + t < n2[j]) q[t] = cp[1 + t];
+#pragma unroll
+              for (int t = 0; t < FVM_FOLD_AHEAD; ++t)
+                if (1 + t < n2[j]) {
+                  ce[j] += q[t].x;  // still in half-edge order
+                  ce[j] += q[t].y;
+                }
+              i = 1 + FVM_FOLD_AHEAD;
+            }
+#endif
 #pragma unroll 1
-        for (int kk = lo; kk < hi; ++kk) {
-          const double ce = s_ce[kk];
-          double el = 0.0;
-          unsigned m = 0xffu;
+            for (; i < n2[j]; ++i) {
+              const double2 p = cp[i];
+              ce[j] += p.x;
+              ce[j] += p.y;
+            }
+          }
+          fvm_edge(u0[j], u1[j], x00[j], x01[j], x02[j], x10[j], x11[j], x12[j], ce[j], 0.0, 0xffu,
+                   aD, aO, aC);
+#else
+          // the edge functor is evaluated per half-edge (edge_length / subdomain bits
+          // vary inside a slot); a padding entry has ce = 0 and mask 0: it adds zeros
+          {
+            const double* s_ce = (const double*)s_ce2;
+#pragma unroll 1
+            for (int h = 2 * lo2[j]; h < 2 * (lo2[j] + n2[j]); ++h) {
+              const double c1 = s_ce[h];
+              double el = 0.0;
+              unsigned m = 0xffu;
 #if FVM_EDGE_USES_EL
-          el = s_el[kk];
+              el = s_el[h];
 #endif
 #if FVM_EDGE_MASKED
-          m = s_mask[kk];
+              m = s_mask[h];
 #endif
-          double D = 0.0, O = 0.0, C = 0.0;
-          fvm_edge(u0, u1, x00, x01, x02, x10, x11, x12, ce, el, m, D, O, C);
-          aD += D;
-          aO += O;
-          aC += C;
-        }
+              double D = 0.0, O = 0.0, C = 0.0;
+              fvm_edge(u0[j], u1[j], x00[j], x01[j], x02[j], x10[j], x11[j], x12[j], c1, el, m, D,
+                       O, C);
+              aD += D;
+              aO += O;
+              aC += C;
+            }
+          }
 #endif
+          if (act[j]) {
 #if FVM_MODE == FVM_MODE_LINEAR || FVM_MODE == FVM_MODE_JACOBIAN
-        a.data[d_s0 + s] = aO;  // consecutive lanes, (nearly) consecutive slots: coalesced
+            a.data[d_s0 + sl[j]] = aO;  // consecutive lanes, (nearly) consecutive slots: coalesced
 #endif
-        // parked at k + g: a row's shares stay contiguous and the row stride is the CSR
-        // row length (4 + 1 / 8 + 1 on the zigzag triangle grid: odd, so the row pass
-        // below reads conflict-free; the compact stride 4 / 8 would 4-way conflict)
+            // parked at k + g: a row's shares stay contiguous and the row stride is the CSR
+            // row length (4 + 1 / 8 + 1 on the zigzag triangle grid: odd, so the row pass
+            // below reads conflict-free; the compact stride 4 / 8 would 4-way conflict)
 #if FVM_ACC_D
-        s_accd[k + g] = aD;
+            s_accd[kk[j] + g[j]] = aD;
 #endif
 #if FVM_ACC_C
-        s_accc[k + g] = aC;
+            s_accc[kk[j] + g[j]] = aC;
 #endif
+          }
+        }
       }
       // the parked shares (and pass A's CSR stores) are visible to all math warps
       asm volatile("bar.sync 1, %0;" ::"n"(FVM_NCT) : "memory");
 
       // ---------------- pass B: one lane per matrix row ------------------------
-#if FVM_ROW_RUNS  // (experiment: equal runs of rows per warp)
-      for (int g = ra + lane; g < rb; g += 32) {
-#else
-      for (int g = rblock * 32 + lane; g < d_nr; g += FVM_NCT) {
-#endif
+      for (int g = g_first + lane; g < g_end; g += g_step) {
         const int b = s_rp[g] - d_s0, e = s_rp[g + 1] - d_s0;  // CSR slots of the row
         double sD = 0.0, sC = 0.0;
+        int k = b;
+#if FVM_ROW_AHEAD > 0
+        {
+          // the first shares of the row are loaded together, then added in slot order (a
+          // share past the row's end reads as +0.0: exact); the loop below takes the rest
+          double vD[FVM_ROW_AHEAD], vC[FVM_ROW_AHEAD];
+#pragma unroll
+          for (int t = 0; t < FVM_ROW_AHEAD; ++t) {
+            vD[t] = vC[t] = 0.0;
+            if (b + t < e - 1) {
+#if FVM_ACC_D
+              vD[t] = s_accd[b + t];
+#endif
+#if FVM_ACC_C
+              vC[t] = s_accc[b + t];
+#endif
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < FVM_ROW_AHEAD; ++t) {
+#if FVM_ACC_D
+            sD += vD[t];
+#endif
+#if FVM_ACC_C
+            sC += vC[t];
+#endif
+          }
+          k = b + FVM_ROW_AHEAD;
+        }
+#endif
 #pragma unroll 1
-        for (int k = b; k < e - 1; ++k) {  // its off-diagonal slots, in slot order
+        for (; k < e - 1; ++k) {  // its (remaining) off-diagonal slots, in slot order
 #if FVM_ACC_D
           sD += s_accd[k];
 #endif

@@ -457,18 +457,18 @@ class DeviceMesh:
 
     def stats(self):
         """Layout diagnostics of the device mesh (see ``fvm_mesh_stats``)."""
-        out = (c_int64 * 8)()
-        self.eng._ck(self.eng.lib.fvm_mesh_stats(self.handle, out, 8))
+        out = (c_int64 * 9)()
+        self.eng._ck(self.eng.lib.fvm_mesh_stats(self.handle, out, 9))
         keys = ["max_he", "max_slots", "max_rows", "max_xtab", "uncovered_slots", "quantum",
-                "tiles", "halfedges"]
+                "tiles", "halfedges", "padded_halfedges"]
         return dict(zip(keys, [int(x) for x in out]))
 
     def layout(self):
         """Host copies of the device layout (tests / inspection): tile descriptors,
-        packed slot metadata, ce_ratios in half-edge order."""
+        packed slot metadata, ce_ratios in (padded) half-edge order."""
         tiles = numpy.empty(self.n_tiles, dtype=self.TILE_DTYPE)
         meta = numpy.empty(self.nnz - self.n_rows, dtype=numpy.uint32)
-        ce = numpy.empty(self.n_halfedges, dtype=numpy.float64)
+        ce = numpy.empty(self.stats()["padded_halfedges"], dtype=numpy.float64)
         for which, arr in ((0, tiles), (1, meta), (2, ce)):
             self.eng._ck(
                 self.eng.lib.fvm_mesh_debug_copy(self.handle, which, _ptr(arr), arr.nbytes)

@@ -241,6 +241,7 @@ def test_out_of_range_endpoint_is_refused():
     from pyfvm_b200 import engine, meshes
 
     mesh = meshes.Mesh(*problems.rectangle(9, 7))
+    mesh.ce_ratios, mesh.control_volumes, mesh.is_boundary_point  # geometry of the intact mesh
     idx = numpy.array(mesh.idx_hierarchy)
     idx[1, 0, 3] = len(mesh.points) + 5
     mesh._idx = idx

@@ -1,11 +1,15 @@
-"""Development tool: sweep the tile kernel's launch shape on one mesh.
+"""Development tool: time the tile kernel on one mesh for several modes and tuning
+variants (same box, back to back: kernel changes are judged by same-box A/B only).
 
-  python tools/sweep_tile.py --size 4001 --quantum 1536,2048,3072 --warps 4,8 --stages 2,3
+  python tools/sweep_tile.py --size 4001 --modes 0,1,2,3 --quantum 3432 \
+      --variants "row_runs=0;row_runs=1;fold_ahead=0,consumer_warps=8"
+  python tools/sweep_tile.py --cube 200 --modes 1,2 --variants "fold_ahead=0;fold_ahead=5"
 
-Prints one line per combination: ms per assembly launch, algorithmic GB/s and
-registers.  Not part of the product or the tests."""
+A variant is a comma-separated list of codegen.tuning overrides; "" is the default.
+Mode 3 = SpMV on the assembled system (needs mode 0 in the same run order-independent:
+it assembles once itself).  Prints one line per (quantum, mode, variant): ms per launch,
+algorithmic GB/s, fraction of the measured HBM peak.  Not part of the product or tests."""
 import argparse
-import itertools
 import os
 import sys
 
@@ -15,74 +19,94 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import bench  # noqa: E402
-from pyfvm_b200 import codegen, engine, form_language, lowering, meshes  # noqa: E402
+from pyfvm_b200 import codegen, engine, form_language, lowering, meshes, solvers  # noqa: E402
+from tests import problems  # noqa: E402
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=4001)
-    ap.add_argument("--cube", type=int, default=0, help="use a cube_tetra mesh with this many points per side")
-    ap.add_argument("--quantum", default="3072")
-    ap.add_argument("--warps", default="8")
-    ap.add_argument("--stages", default="2")
-    ap.add_argument("--ctas", default="0")
-    ap.add_argument("--factor", default="1")
+    ap.add_argument("--cube", type=int, default=0, help="cube_tetra mesh (generated on the device)")
+    ap.add_argument("--quantum", default="0")
+    ap.add_argument("--modes", default="0,1")
+    ap.add_argument("--variants", default="")
     ap.add_argument("--fmad", type=int, default=0)
-    ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--steps", type=int, default=50)
     args = ap.parse_args()
     ints = lambda s: [int(x) for x in s.split(",")]
+    variants = []
+    for v in args.variants.split(";"):
+        variants.append({k: int(x) for k, x in (kv.split("=") for kv in v.split(",") if kv)})
+    peak, _ = bench.measured_peak()
 
     eng = engine.Engine.get()
     if args.cube:
-        xs = numpy.linspace(0.0, 1.0, args.cube)
-        mesh = meshes.Mesh(*meshes.cube_tetra(xs, xs, xs))
-        from tests import problems
+        from pyfvm_b200 import device_meshes
 
-        prob = problems.poisson(form_language) if args.mode == 0 else problems.bratu(form_language)
+        xs = numpy.linspace(0.0, 1.0, args.cube)
+        mesh = device_meshes.device_cube_tetra(xs, xs, xs)
+        lin, nonlin, dim, cdim = problems.poisson, problems.bratu, 3, 3
     else:
         xs = numpy.linspace(0.0, 1.0, args.size)
         mesh = meshes.Mesh(*meshes.rectangle_tri(xs, xs))
-        prob = bench.problem_c4(form_language)
-    dim = 3 if args.cube else 2
-    lowered = (lowering.lower_linear if args.mode == 0 else lowering.lower_nonlinear)(prob, dim)
+        lin = nonlin = bench.problem_c4
+        dim, cdim = 2, 2
     n = len(mesh.points)
     dirid = numpy.zeros(n, dtype=numpy.uint8)
     dirid[mesh.is_boundary_point] = 1
-    d_dir = eng.to_device(dirid)
-    u = eng.to_device(numpy.random.default_rng(0).standard_normal(n))
+    d_dir = eng.to_device(dirid, pad=16)
+    u = eng.to_device(0.1 * numpy.random.default_rng(0).standard_normal(n), pad=16)
+    low = {0: lowering.lower_linear(lin(form_language), dim)}
+    low[1] = low[2] = lowering.lower_nonlinear(nonlin(form_language), dim)
     for q in ints(args.quantum):
         dm = engine.DeviceMesh(eng, mesh, need_el=False, tile_quantum=q)
-        print(dm.stats(), flush=True)
-        data = eng.alloc(8 * dm.nnz)
-        vec = eng.alloc(8 * n)
-        for w, st, ct, fc in itertools.product(
-            ints(args.warps), ints(args.stages), ints(args.ctas), ints(args.factor)
-        ):
-            fun = codegen.generate(
-                lowered, args.mode, [None] * len(lowered.edge), [None] * len(lowered.vertex),
-                tune={"consumer_warps": w, "stages": st, "ctas_per_sm": ct, "factor_ce": fc},
-            )
-            try:
-                k = eng.kernel(fun, fmad=bool(args.fmad))
-                for _ in range(5):
-                    dm.launch(k, dirid=d_dir.ptr, u=u.ptr, data=data.ptr, vec=vec.ptr)
-                eng.timer_begin()
-                for _ in range(args.steps):
-                    dm.launch(k, dirid=d_dir.ptr, u=u.ptr, data=data.ptr, vec=vec.ptr)
-                ms = eng.timer_end() / args.steps
-            except engine.FvmError as e:
-                print(f"q={q} warps={w} stages={st} ctas={ct} factor={fc}: FAILED {str(e)[:100]}")
-                continue
-            alg = bench.algorithmic_bytes(
-                dm.R, dm.nnz, n, dim, fun.uses_x, fun.uses_el, "assembly" if args.mode != 1 else "residual"
-            )
-            print(
-                f"q={q} warps={w} stages={st} ctas={ct} factor={fc} fmad={args.fmad}: {ms:.4f} ms  "
-                f"{alg / ms / 1e6:.0f} GB/s alg  {dm.R / ms / 1e6:.1f} Gcontrib/s  "
-                f"{k.info(dm)} tiles={dm.n_tiles}",
-                flush=True,
-            )
+        st = dm.stats()
+        print(st, f"tiles={dm.n_tiles} build_ms={dm.build_ms:.1f}", flush=True)
+        data = eng.alloc(8 * dm.nnz + 16)
+        vec = eng.alloc(8 * n + 16)
+        R = dm.n_halfedges / 2.0
+        for mode in ints(args.modes):
+            for tv in variants:
+                tune = codegen.tuning(cdim)
+                tune.update(tv)
+                try:
+                    if mode == 3:
+                        if tv:
+                            continue  # the SpMV kernel has a fixed prelude
+                        k0 = eng.kernel(codegen.generate(low[0], 0, [None], [None], codegen.tuning(cdim)))
+                        dm.launch(k0, dirid=d_dir.ptr, u=u.ptr, data=data.ptr, vec=vec.ptr)
+                        sysm = solvers.DeviceSystem(dm, data.ptr)
+                        y = eng.alloc(8 * n + 16)
+                        run = lambda: sysm.matvec(u.ptr, y.ptr)
+                        alg = 12 * dm.nnz + 20 * n
+                        info = {}
+                    else:
+                        lw = low[mode]
+                        fun = codegen.generate(
+                            lw, mode, [None] * len(lw.edge), [None] * len(lw.vertex), tune
+                        )
+                        k = eng.kernel(fun, fmad=bool(args.fmad))
+                        run = lambda: dm.launch(k, dirid=d_dir.ptr, u=u.ptr, data=data.ptr, vec=vec.ptr)
+                        alg = bench.algorithmic_bytes(
+                            R, dm.nnz, n, dim, fun.uses_x, fun.uses_el,
+                            "residual" if mode == 1 else "assembly",
+                        )
+                        info = k.info(dm)
+                    for _ in range(5):
+                        run()
+                    eng.timer_begin()
+                    for _ in range(args.steps):
+                        run()
+                    ms = eng.timer_end() / args.steps
+                except engine.FvmError as e:
+                    print(f"q={q} mode={mode} {tv}: FAILED {str(e)[:200]}", flush=True)
+                    continue
+                print(
+                    f"q={st['quantum']} mode={mode} {tv or 'default'}: {ms:.4f} ms  "
+                    f"{alg / ms / 1e6:.0f} GB/s alg  frac={alg / ms / 1e6 / peak:.3f}  "
+                    f"{R / ms / 1e6:.1f} Gcontrib/s  {info}",
+                    flush=True,
+                )
         del dm, data, vec
 
 
