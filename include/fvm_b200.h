@@ -181,6 +181,7 @@ typedef struct fvm_kernel_opts {
   int32_t consumer_warps; /* math warps per CTA (1..16); = FVM_CONSUMER_WARPS           */
   int32_t stages;         /* shared-memory ring depth; must equal FVM_STAGES        */
   int32_t ctas_per_sm;    /* persistent CTAs per SM, 0 = as many as fit             */
+  int32_t producers;      /* producer warps per CTA (1, 2 or 4); = FVM_PRODUCERS    */
 } fvm_kernel_opts;
 int fvm_kernel_create(fvm_ctx* ctx, const char* functor_src, const fvm_kernel_opts* opts,
                       fvm_kernel** out);

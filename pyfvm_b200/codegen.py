@@ -28,6 +28,9 @@ def tuning(cell_dim=2):
     return {
         "consumer_warps": int(os.environ.get("FVM_CONSUMER_WARPS", "4")),
         "stages": int(os.environ.get("FVM_STAGES", "2")),
+        # producer warps per CTA: the stage fill is split into four roles (half-edge streams,
+        # row streams, coordinate table, u table) issued in parallel
+        "producers": int(os.environ.get("FVM_PRODUCERS", "1")),
         "ctas_per_sm": int(os.environ.get("FVM_CTAS_PER_SM", "0")),
         # fold the ce_ratios of a slot first and evaluate ce*g(slot) once
         "factor_ce": int(os.environ.get("FVM_FACTOR_CE", "1")),
@@ -40,6 +43,9 @@ def tuning(cell_dim=2):
         # slot pass: 32-slot chunks a warp keeps in flight together; row pass: shares loaded
         # ahead of the in-order adds (-1: template defaults)
         "ilp": int(os.environ.get("FVM_ILP", "-1")),
+        "setmaxnreg": int(os.environ.get("FVM_SETMAXNREG", "-1")),
+        # tiles ahead of the shared-memory fill whose streams are prefetched into L2
+        "l2_ahead": int(os.environ.get("FVM_L2_AHEAD", "-1")),
         "row_ahead": int(os.environ.get("FVM_ROW_AHEAD", "-1")),
         # (2: decided per tile by its row count -- the template's default)
         "row_runs": int(os.environ.get("FVM_ROW_RUNS", "2")),
@@ -147,6 +153,7 @@ class Functors:
     consumer_warps: int
     stages: int
     ctas_per_sm: int
+    producers: int
     factored: bool
     uses_el: bool
     uses_x: bool
@@ -200,6 +207,7 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         "FVM_FLAGS": f"{flags}u",
         "FVM_CONSUMER_WARPS": tune["consumer_warps"],
         "FVM_STAGES": tune["stages"],
+        "FVM_PRODUCERS": tune["producers"],
         "FVM_EDGE_FACTORED": int(factored),
         "FVM_MIN_CTAS": tune["min_ctas"],
         "FVM_ROW_RUNS": tune["row_runs"],
@@ -215,7 +223,8 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
     if bad:
         raise ValueError(f"undefined functions cannot be lowered to device code: {sorted(bad)}")
 
-    for key, macro in (("fold_ahead", "FVM_FOLD_AHEAD"), ("ilp", "FVM_ILP"), ("row_ahead", "FVM_ROW_AHEAD")):
+    for key, macro in (("fold_ahead", "FVM_FOLD_AHEAD"), ("ilp", "FVM_ILP"), ("row_ahead", "FVM_ROW_AHEAD"),
+                       ("setmaxnreg", "FVM_SETMAXNREG"), ("l2_ahead", "FVM_L2_AHEAD")):
         if tune.get(key, -1) >= 0:
             defs[macro] = tune[key]
     L = [f"// generated by pyfvm_b200.codegen (mode {mode}); do not edit"]
@@ -265,6 +274,7 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         consumer_warps=tune["consumer_warps"],
         stages=tune["stages"],
         ctas_per_sm=tune["ctas_per_sm"],
+        producers=tune["producers"],
         factored=factored,
         uses_el=bool(flags & F_EDGE_EL),
         uses_x=bool(flags & F_X),

@@ -64,12 +64,14 @@ struct FvmTileDesc {  // 128 bytes, one per tile
 #define FVM_TILE_MAX_XTAB 2046  // vertex-table entries per tile
 
 // Dynamic shared-memory carve-up of one CTA, identical on host and device:
-//   [full/empty mbarriers][stage 0][stage 1]...
+//   [full/empty mbarriers][descriptor-ring mbarriers][descriptor rings][stage 0][stage 1]...
 // The stream offsets (desc .. vmask) are relative to the start of a stage.
 // Every staged stream gets 16 spare bytes: its bulk copy starts at the 16B
 // boundary below the first element and is rounded up to 16B.
+#define FVM_NDESC 3  // tile descriptors a producer warp keeps in flight (its descriptor ring)
 struct FvmSmemLayout {
   unsigned bar, stage0, stage_bytes;
+  unsigned dbar, ring;  // per producer warp: FVM_NDESC mbarriers / 128-byte descriptor slots
   // within a stage (accd / accc: per-slot diagonal / rhs contributions waiting for
   // the row fold; dg: offset of the diagonal slot inside every row)
   unsigned desc, ce, el, mask, meta, rowptr, cv, xy, u, dir, vmask, accd, accc, dg, mat;
@@ -142,14 +144,15 @@ FVM_HD inline unsigned fvm_coord_stride(int dim) { return dim == 2 ? 2u : 4u; }
 // have one entry per off-diagonal slot)
 FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_rows, int max_xtab,
                                             int dim, unsigned flags, int mode, int stages,
-                                            int max_csr_slots) {
+                                            int max_csr_slots, int producers) {
   FvmSmemLayout L;
   const unsigned he = (unsigned)max_he, sl = (unsigned)max_slots, nr = (unsigned)max_rows;
   unsigned o = 0;  // within a stage
   const unsigned xt = (unsigned)max_xtab;
   L.desc = o;   o += 128;
-  L.ce = o;     o += (mode != FVM_MODE_SPMV) ? fvm_round16(he * 8u) + 16u : 0u;
-  L.el = o;     o += (flags & FVM_F_EDGE_EL) ? fvm_round16(he * 8u) + 16u : 0u;
+  // (the half-edge streams of a tile start 16-byte aligned: no slack)
+  L.ce = o;     o += (mode != FVM_MODE_SPMV) ? fvm_round16(he * 8u) : 0u;
+  L.el = o;     o += (flags & FVM_F_EDGE_EL) ? fvm_round16(he * 8u) : 0u;
   L.mask = o;   o += (flags & FVM_F_EDGE_MASK) ? fvm_round16(he) + 16u : 0u;
   L.meta = o;   o += fvm_round16(sl * 4u) + 16u;
   L.rowptr = o; o += fvm_round16((nr + 1u) * 4u) + 16u;
@@ -164,8 +167,10 @@ FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_r
   L.dg = o;     o += (mode != FVM_MODE_RESIDUAL) ? fvm_round16(nr * 2u) + 16u : 0u;
   L.mat = o;    o += (mode == FVM_MODE_SPMV) ? fvm_round16((unsigned)max_csr_slots * 8u) + 16u : 0u;
   L.stage_bytes = o;
-  L.bar = 0;
-  L.stage0 = fvm_round16(16u * (unsigned)stages);  // 2 x 8B mbarriers per stage
+  L.bar = 0;  // 2 x 8B mbarriers per stage, then the descriptor-ring mbarriers and slots
+  L.dbar = fvm_round16(16u * (unsigned)stages);
+  L.ring = fvm_round16(L.dbar + 8u * FVM_NDESC * (unsigned)producers);
+  L.stage0 = L.ring + 128u * FVM_NDESC * (unsigned)producers;
   o = L.stage0 + L.stage_bytes * (unsigned)stages;
   L.total = o;
   return L;

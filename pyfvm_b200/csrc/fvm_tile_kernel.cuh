@@ -65,8 +65,17 @@
 #define FVM_ACC_C ((FVM_FLAGS & FVM_F_EDGE_C) != 0)
 
 #define FVM_XS (FVM_DIM == 2 ? 2 : 4)       // doubles per vertex in the coordinate arrays
-#define FVM_NCT (32 * FVM_CONSUMER_WARPS)  // consumer threads
-#define FVM_THREADS (FVM_NCT + 32)         // + one producer warp
+#ifndef FVM_PRODUCERS
+#define FVM_PRODUCERS 1  // producer warps (one elected lane each); 1, 2 or 4
+#endif
+#define FVM_NCT (32 * FVM_CONSUMER_WARPS)            // consumer threads
+#define FVM_THREADS (FVM_NCT + 32 * FVM_PRODUCERS)   // + the producer warps
+// experiment: register reallocation between the warpgroups (setmaxnreg; the producer
+// warpgroup keeps 40 registers, the math warpgroup takes 88).  ptxas fits the math path
+// into the launch's 64 registers anyway, so it is off by default.
+#ifndef FVM_SETMAXNREG
+#define FVM_SETMAXNREG 0
+#endif
 #define FVM_FULL 0xffffffffu
 #ifndef FVM_ROW_RUNS
 // pass B row dealing: 0 = 32-row blocks round-robin over the warps, 1 = equal runs of rows
@@ -74,8 +83,11 @@
 // tiles give every warp 26 rows; ~17-row tetrahedral tiles keep one warp's lanes busy)
 #define FVM_ROW_RUNS 2
 #endif
+#ifndef FVM_L2_AHEAD
+#define FVM_L2_AHEAD 0  // experiment (measured: hurts): tiles ahead whose streams are prefetched into L2
+#endif
 #ifndef FVM_ILP
-#define FVM_ILP 2  // 32-slot chunks a warp keeps in flight together in the slot pass
+#define FVM_ILP 1  // 32-slot chunks a warp keeps in flight together in the slot pass (2: measured, no gain)
 #endif
 #ifndef FVM_ROW_AHEAD
 #define FVM_ROW_AHEAD 6  // parked shares of a row loaded before the in-order adds start
@@ -186,124 +198,261 @@ __device__ __noinline__ void fvm_halo_acquire(const FvmTileArgs& a) {
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 
+// L2 prefetch of a contiguous stream (cp.async.bulk.prefetch.L2): the DRAM -> L2 leg of a
+// tile's streams is started FVM_L2_AHEAD tiles before the shared-memory fill, so the fill
+// of the 2-stage ring waits for an L2 hit, not for DRAM under load.
+__device__ __forceinline__ void fvm_l2_prefetch(const void* g, unsigned nbytes) {
+  const unsigned long long a = (unsigned long long)g;
+  const unsigned shift = (unsigned)(a & 15ull);
+  const unsigned bytes = fvm_round16(shift + nbytes);
+  if (nbytes)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a - shift), "r"(bytes) : "memory");
+}
+
+// The stage fill is split into four ROLES so that several producer warps can issue it in
+// parallel (the serial issue time of ~20 bulk copies per tile -- 8 halo ranges for each of
+// the two vertex tables on tetrahedra -- is on the critical path of the 2-stage ring):
+//   role 0 (HE)  : ce_ratio / edge_length / mask per half-edge (SpMV: CSR values), slot_meta
+//   role 1 (ROW) : the tile descriptor, row pointers, cv, Dirichlet ids, diagonal offsets, vmask
+//   role 2 (XY)  : vertex table of coordinates (own rows + halo ranges)
+//   role 3 (U)   : vertex table of u (own rows + halo ranges), after the fused halo wait
+// Producer warp p of P takes the roles r with r % P == p; it adds the bytes of its roles
+// to the stage's full barrier with ONE arrive.expect_tx (the barrier counts P arrivals).
+// `rd` points at the descriptor in the warp's own descriptor ring (shared memory).
+#define FVM_ROLE_MINE(r, p) (((r) % FVM_PRODUCERS) == (p))
+
+template <int P_ID>
 __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemLayout& L,
                                             unsigned char* stage, void* full,
-                                            const FvmTileDesc& d, bool& halo_ready) {
-  const int v0 = a.row_base + d.r0;
-  *(FvmTileDesc*)(stage + L.desc) = d;
+                                            const FvmTileDesc* rd, bool wait_empty, void* empty,
+                                            unsigned empty_parity, bool& halo_ready) {
+  const int d_r0 = rd->r0, d_nr = rd->nr, d_s0 = rd->s0, d_nsl = rd->nsl, d_nhe = rd->nhe;
+  const long long d_h0 = rd->h0;
+  const int d_own_start = rd->own_start, d_own_count = rd->own_count, nhalo = rd->nhalo;
+  const int v0 = a.row_base + d_r0;
   unsigned total = 0;
+  // ---- sizes first (nothing below touches the stage before the empty wait)
 #if FVM_MODE != FVM_MODE_SPMV
-  const FvmStage g_ce = fvm_stage(a.he_ce + d.h0, (unsigned)d.nhe * 8u);
+  const FvmStage g_ce = fvm_stage(a.he_ce + d_h0, (unsigned)d_nhe * 8u);
 #else
-  const FvmStage g_ce = fvm_stage(a.mat + d.s0, (unsigned)d.nsl * 8u);  // CSR values instead
+  const FvmStage g_ce = fvm_stage(a.mat + d_s0, (unsigned)d_nsl * 8u);  // CSR values instead
 #endif
-  const FvmStage g_meta = fvm_stage(a.slot_meta + (d.s0 - d.r0), (unsigned)(d.nsl - d.nr) * 4u);
-  const FvmStage g_rp = fvm_stage(a.indptr + d.r0, (unsigned)(d.nr + 1) * 4u);
-  total += g_ce.bytes + g_meta.bytes + g_rp.bytes;
+  const FvmStage g_meta = fvm_stage(a.slot_meta + (d_s0 - d_r0), (unsigned)(d_nsl - d_nr) * 4u);
+  const FvmStage g_rp = fvm_stage(a.indptr + d_r0, (unsigned)(d_nr + 1) * 4u);
+  if (FVM_ROLE_MINE(0, P_ID)) total += g_ce.bytes + g_meta.bytes;
+  if (FVM_ROLE_MINE(1, P_ID)) total += g_rp.bytes;
   // vertex table: own rows, then the halo ranges (even starts, even counts)
-  unsigned n_tab = (unsigned)d.own_count;
-  const FvmTileDesc* sd = (const FvmTileDesc*)(stage + L.desc);  // dynamic indexing: from smem
-  const int nhalo = d.nhalo;
+  unsigned n_tab = (unsigned)d_own_count;
 #pragma unroll 1
-  for (int i = 0; i < nhalo; ++i) n_tab += sd->hcount[i];
+  for (int i = 0; i < nhalo; ++i) n_tab += rd->hcount[i];
 #if FVM_EDGE_USES_EL
-  const FvmStage g_el = fvm_stage(a.he_el + d.h0, (unsigned)d.nhe * 8u);
-  total += g_el.bytes;
+  const FvmStage g_el = fvm_stage(a.he_el + d_h0, (unsigned)d_nhe * 8u);
+  if (FVM_ROLE_MINE(0, P_ID)) total += g_el.bytes;
 #endif
 #if FVM_EDGE_MASKED
-  const FvmStage g_mask = fvm_stage(a.he_mask + d.h0, (unsigned)d.nhe);
-  total += g_mask.bytes;
+  const FvmStage g_mask = fvm_stage(a.he_mask + d_h0, (unsigned)d_nhe);
+  if (FVM_ROLE_MINE(0, P_ID)) total += g_mask.bytes;
 #endif
 #if FVM_STAGE_CV
-  const FvmStage g_cv = fvm_stage(a.cv + v0, (unsigned)d.nr * 8u);
-  total += g_cv.bytes;
+  const FvmStage g_cv = fvm_stage(a.cv + v0, (unsigned)d_nr * 8u);
+  if (FVM_ROLE_MINE(1, P_ID)) total += g_cv.bytes;
 #endif
 #if FVM_STAGE_X
-  total += n_tab * 8u * FVM_XS;
+  if (FVM_ROLE_MINE(2, P_ID)) total += n_tab * 8u * FVM_XS;
 #endif
 #if FVM_STAGE_U
-  total += n_tab * 8u;
+  if (FVM_ROLE_MINE(3, P_ID)) total += n_tab * 8u;
 #endif
 #if FVM_HAS_DIRICHLET
-  const FvmStage g_dir = fvm_stage(a.dir_id + v0, (unsigned)d.nr);
-  total += g_dir.bytes;
+  const FvmStage g_dir = fvm_stage(a.dir_id + v0, (unsigned)d_nr);
+  if (FVM_ROLE_MINE(1, P_ID)) total += g_dir.bytes;
 #endif
 #if FVM_MODE != FVM_MODE_RESIDUAL
-  const FvmStage g_dg = fvm_stage(a.row_diag + d.r0, (unsigned)d.nr * 2u);
-  total += g_dg.bytes;
+  const FvmStage g_dg = fvm_stage(a.row_diag + d_r0, (unsigned)d_nr * 2u);
+  if (FVM_ROLE_MINE(1, P_ID)) total += g_dg.bytes;
 #endif
 #if FVM_VERT_MASKED
-  const FvmStage g_vm = fvm_stage(a.vmask + v0, (unsigned)d.nr);
-  total += g_vm.bytes;
+  const FvmStage g_vm = fvm_stage(a.vmask + v0, (unsigned)d_nr);
+  if (FVM_ROLE_MINE(1, P_ID)) total += g_vm.bytes;
 #endif
+#if FVM_STAGE_U
+  if (FVM_ROLE_MINE(3, P_ID) && a.n_halo_flags > 0 && !halo_ready) {
+    // does this tile's vertex table reach into the ghost vertices?
+    int tmin = d_own_start, tmax = d_own_start + d_own_count;
+    if (nhalo > 0) {
+      tmin = min(tmin, rd->hstart[0]);
+      tmax = max(tmax, rd->hstart[nhalo - 1] + (int)rd->hcount[nhalo - 1]);
+    }
+    // (a tile with columns outside its table gathers them from global memory: any of
+    // them may be a ghost vertex)
+    if (tmin < a.ghost_lo_end || tmax > a.ghost_hi_begin || rd->uncovered) {
+      fvm_halo_acquire(a);
+      halo_ready = true;
+    }
+  }
+#endif
+  if (wait_empty) fvm_mbar_wait(empty, empty_parity);  // the math warps released the stage
+  if (FVM_ROLE_MINE(1, P_ID)) {
+    const int4* src = (const int4*)rd;
+    int4* dst = (int4*)(stage + L.desc);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dst[i] = src[i];  // .. uncovered; the padding is not read
+  }
   fvm_mbar_expect_tx(full, total);  // release: the descriptor store above is visible
+  if (FVM_ROLE_MINE(0, P_ID)) {
 #if FVM_MODE != FVM_MODE_SPMV
-  if (g_ce.bytes) fvm_bulk_g2s(stage + L.ce, g_ce.src, g_ce.bytes, full);
+    if (g_ce.bytes) fvm_bulk_g2s(stage + L.ce, g_ce.src, g_ce.bytes, full);
 #else
-  if (g_ce.bytes) fvm_bulk_g2s(stage + L.mat, g_ce.src, g_ce.bytes, full);
+    if (g_ce.bytes) fvm_bulk_g2s(stage + L.mat, g_ce.src, g_ce.bytes, full);
 #endif
-  if (g_meta.bytes) fvm_bulk_g2s(stage + L.meta, g_meta.src, g_meta.bytes, full);
-  fvm_bulk_g2s(stage + L.rowptr, g_rp.src, g_rp.bytes, full);
+    if (g_meta.bytes) fvm_bulk_g2s(stage + L.meta, g_meta.src, g_meta.bytes, full);
 #if FVM_EDGE_USES_EL
-  if (g_el.bytes) fvm_bulk_g2s(stage + L.el, g_el.src, g_el.bytes, full);
+    if (g_el.bytes) fvm_bulk_g2s(stage + L.el, g_el.src, g_el.bytes, full);
 #endif
 #if FVM_EDGE_MASKED
-  if (g_mask.bytes) fvm_bulk_g2s(stage + L.mask, g_mask.src, g_mask.bytes, full);
+    if (g_mask.bytes) fvm_bulk_g2s(stage + L.mask, g_mask.src, g_mask.bytes, full);
 #endif
+  }
+  if (FVM_ROLE_MINE(1, P_ID)) {
+    fvm_bulk_g2s(stage + L.rowptr, g_rp.src, g_rp.bytes, full);
 #if FVM_STAGE_CV
-  if (g_cv.bytes) fvm_bulk_g2s(stage + L.cv, g_cv.src, g_cv.bytes, full);
+    if (g_cv.bytes) fvm_bulk_g2s(stage + L.cv, g_cv.src, g_cv.bytes, full);
 #endif
+#if FVM_HAS_DIRICHLET
+    if (g_dir.bytes) fvm_bulk_g2s(stage + L.dir, g_dir.src, g_dir.bytes, full);
+#endif
+#if FVM_MODE != FVM_MODE_RESIDUAL
+    if (g_dg.bytes) fvm_bulk_g2s(stage + L.dg, g_dg.src, g_dg.bytes, full);
+#endif
+#if FVM_VERT_MASKED
+    if (g_vm.bytes) fvm_bulk_g2s(stage + L.vmask, g_vm.src, g_vm.bytes, full);
+#endif
+  }
 #if FVM_STAGE_X
-  {
+  if (FVM_ROLE_MINE(2, P_ID)) {
     unsigned char* dst = stage + L.xy;
     const unsigned vb = 8u * FVM_XS;  // bytes per vertex
-    if (d.own_count)
-      fvm_bulk_g2s(dst, a.coords + (size_t)d.own_start * FVM_XS, (unsigned)d.own_count * vb, full);
-    dst += (unsigned)d.own_count * vb;
+    if (d_own_count)
+      fvm_bulk_g2s(dst, a.coords + (size_t)d_own_start * FVM_XS, (unsigned)d_own_count * vb, full);
+    dst += (unsigned)d_own_count * vb;
 #pragma unroll 1
     for (int i = 0; i < nhalo; ++i) {
-      const unsigned cnt = sd->hcount[i];
-      fvm_bulk_g2s(dst, a.coords + (size_t)sd->hstart[i] * FVM_XS, cnt * vb, full);
+      const unsigned cnt = rd->hcount[i];
+      fvm_bulk_g2s(dst, a.coords + (size_t)rd->hstart[i] * FVM_XS, cnt * vb, full);
       dst += cnt * vb;
     }
   }
 #endif
 #if FVM_STAGE_U
-  {
-    if (a.n_halo_flags > 0 && !halo_ready) {
-      // does this tile's vertex table reach into the ghost vertices?
-      int tmin = d.own_start, tmax = d.own_start + d.own_count;
-      if (nhalo > 0) {
-        tmin = min(tmin, sd->hstart[0]);
-        tmax = max(tmax, sd->hstart[nhalo - 1] + (int)sd->hcount[nhalo - 1]);
-      }
-      // (a tile with columns outside its table gathers them from global memory: any of
-      // them may be a ghost vertex)
-      if (tmin < a.ghost_lo_end || tmax > a.ghost_hi_begin || d.uncovered) {
-        fvm_halo_acquire(a);
-        halo_ready = true;
-      }
-    }
+  if (FVM_ROLE_MINE(3, P_ID)) {
     unsigned char* dst = stage + L.u;
-    if (d.own_count) fvm_bulk_g2s(dst, a.u + d.own_start, (unsigned)d.own_count * 8u, full);
-    dst += (unsigned)d.own_count * 8u;
+    if (d_own_count) fvm_bulk_g2s(dst, a.u + d_own_start, (unsigned)d_own_count * 8u, full);
+    dst += (unsigned)d_own_count * 8u;
 #pragma unroll 1
     for (int i = 0; i < nhalo; ++i) {
-      const unsigned cnt = sd->hcount[i];
-      fvm_bulk_g2s(dst, a.u + sd->hstart[i], cnt * 8u, full);
+      const unsigned cnt = rd->hcount[i];
+      fvm_bulk_g2s(dst, a.u + rd->hstart[i], cnt * 8u, full);
       dst += cnt * 8u;
     }
   }
 #endif
+}
+
+template <int P_ID>
+__device__ __forceinline__ void fvm_prefetch_tile(const FvmTileArgs& a, const FvmTileDesc* rd) {
+  const int d_r0 = rd->r0, d_nr = rd->nr, d_s0 = rd->s0, d_nsl = rd->nsl, d_nhe = rd->nhe;
+  const long long d_h0 = rd->h0;
+  const int v0 = a.row_base + d_r0;
+  if (FVM_ROLE_MINE(0, P_ID)) {
+#if FVM_MODE != FVM_MODE_SPMV
+    fvm_l2_prefetch(a.he_ce + d_h0, (unsigned)d_nhe * 8u);
+#else
+    fvm_l2_prefetch(a.mat + d_s0, (unsigned)d_nsl * 8u);
+#endif
+    fvm_l2_prefetch(a.slot_meta + (d_s0 - d_r0), (unsigned)(d_nsl - d_nr) * 4u);
+#if FVM_EDGE_USES_EL
+    fvm_l2_prefetch(a.he_el + d_h0, (unsigned)d_nhe * 8u);
+#endif
+#if FVM_EDGE_MASKED
+    fvm_l2_prefetch(a.he_mask + d_h0, (unsigned)d_nhe);
+#endif
+  }
+  if (FVM_ROLE_MINE(1, P_ID)) {
+    fvm_l2_prefetch(a.indptr + d_r0, (unsigned)(d_nr + 1) * 4u);
+#if FVM_STAGE_CV
+    fvm_l2_prefetch(a.cv + v0, (unsigned)d_nr * 8u);
+#endif
 #if FVM_HAS_DIRICHLET
-  if (g_dir.bytes) fvm_bulk_g2s(stage + L.dir, g_dir.src, g_dir.bytes, full);
+    fvm_l2_prefetch(a.dir_id + v0, (unsigned)d_nr);
 #endif
 #if FVM_MODE != FVM_MODE_RESIDUAL
-  if (g_dg.bytes) fvm_bulk_g2s(stage + L.dg, g_dg.src, g_dg.bytes, full);
+    fvm_l2_prefetch(a.row_diag + d_r0, (unsigned)d_nr * 2u);
 #endif
 #if FVM_VERT_MASKED
-  if (g_vm.bytes) fvm_bulk_g2s(stage + L.vmask, g_vm.src, g_vm.bytes, full);
+    fvm_l2_prefetch(a.vmask + v0, (unsigned)d_nr);
 #endif
+  }
+  // vertex tables: the tile's own rows and its LAST halo range (the highest vertices: on a
+  // lexicographic numbering the only part no earlier tile has pulled into L2 yet)
+#if FVM_STAGE_X
+  if (FVM_ROLE_MINE(2, P_ID)) {
+    fvm_l2_prefetch(a.coords + (size_t)rd->own_start * FVM_XS, (unsigned)rd->own_count * 8u * FVM_XS);
+    const int nh = rd->nhalo;
+    if (nh > 0)
+      fvm_l2_prefetch(a.coords + (size_t)rd->hstart[nh - 1] * FVM_XS,
+                      (unsigned)rd->hcount[nh - 1] * 8u * FVM_XS);
+  }
+#endif
+#if FVM_STAGE_U
+  if (FVM_ROLE_MINE(3, P_ID) && a.n_halo_flags == 0) {  // (ghost values may still be in flight)
+    fvm_l2_prefetch(a.u + rd->own_start, (unsigned)rd->own_count * 8u);
+    const int nh = rd->nhalo;
+    if (nh > 0) fvm_l2_prefetch(a.u + rd->hstart[nh - 1], (unsigned)rd->hcount[nh - 1] * 8u);
+  }
+#endif
+}
+
+// One producer warp: walks the CTA's tiles, keeps FVM_NDESC tile descriptors in flight
+// in its own shared-memory ring (fetched by bulk copies, so the ~1 us DRAM latency of a
+// descriptor is never waited for) and fills its roles of every stage.
+template <int P_ID>
+__device__ __forceinline__ void fvm_producer_warp(const FvmTileArgs& a, const FvmSmemLayout& L,
+                                                  unsigned char* sm, unsigned long long* full,
+                                                  unsigned long long* empty) {
+  unsigned char* ring = sm + L.ring + P_ID * (FVM_NDESC * 128);
+  unsigned long long* dbar = (unsigned long long*)(sm + L.dbar) + P_ID * FVM_NDESC;
+  // tile t of the walk is tile (t + tile_rot) mod ntiles of the mesh
+  auto rot = [&](int i) { return i + a.tile_rot < a.ntiles ? i + a.tile_rot : i + a.tile_rot - a.ntiles; };
+  auto fetch = [&](int slot, int tile) {
+    fvm_mbar_expect_tx(dbar + slot, 128u);
+    fvm_bulk_g2s(ring + slot * 128, a.tiles + rot(tile), 128u, dbar + slot);
+  };
+#pragma unroll
+  for (int j = 0; j < FVM_NDESC; ++j) {
+    const long long tj = (long long)blockIdx.x + (long long)j * gridDim.x;
+    if (tj < a.ntiles) fetch(j, (int)tj);
+  }
+  bool halo_ready = false;
+  int it = 0;
+  for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+    const int ds = it % FVM_NDESC, st = it % FVM_STAGES;
+    fvm_mbar_wait(dbar + ds, (it / FVM_NDESC) & 1);
+    fvm_produce<P_ID>(a, L, sm + L.stage0 + st * L.stage_bytes, full + st,
+                      (const FvmTileDesc*)(ring + ds * 128), it >= FVM_STAGES, empty + st,
+                      ((it / FVM_STAGES) - 1) & 1, halo_ready);
+    // every read of the ring slot above fed an instruction already issued: refill it
+    const long long tn = (long long)t + (long long)FVM_NDESC * gridDim.x;
+    if (tn < a.ntiles) fetch(ds, (int)tn);
+#if FVM_L2_AHEAD > 0
+    // start the DRAM -> L2 leg of the tile FVM_L2_AHEAD steps ahead (its descriptor was
+    // fetched FVM_NDESC - FVM_L2_AHEAD steps ago)
+    if ((long long)t + (long long)FVM_L2_AHEAD * gridDim.x < a.ntiles) {
+      const int ps = (it + FVM_L2_AHEAD) % FVM_NDESC;
+      fvm_mbar_wait(dbar + ps, ((it + FVM_L2_AHEAD) / FVM_NDESC) & 1);
+      fvm_prefetch_tile<P_ID>(a, (const FvmTileDesc*)(ring + ps * 128));
+    }
+#endif
+  }
 }
 
 // Columns a tile's halo ranges do not cover (irregular numbering) are gathered
@@ -330,26 +479,13 @@ __device__ __noinline__ double4 fvm_gather_column(const int* colidx, const doubl
   return r;
 }
 
-__device__ __forceinline__ FvmTileDesc fvm_load_desc(const FvmTileDesc* g) {
-  FvmTileDesc d;
-  const int4 d0 = __ldg((const int4*)g), d1 = __ldg((const int4*)g + 1);
-  const int4 d2 = __ldg((const int4*)g + 2), d3 = __ldg((const int4*)g + 3);
-  const int4 d4 = __ldg((const int4*)g + 4), d5 = __ldg((const int4*)g + 5);
-  ((int4*)&d)[0] = d0;
-  ((int4*)&d)[1] = d1;
-  ((int4*)&d)[2] = d2;
-  ((int4*)&d)[3] = d3;
-  ((int4*)&d)[4] = d4;
-  ((int4*)&d)[5] = d5;  // .. hcount; the padding is not read
-  return d;
-}
-
-// FVM_MIN_CTAS > 0 makes the register allocation fit that many CTAs per SM; measured
-// on C4: unset (72 registers, 5 CTAs/SM) beats both 6 CTAs (64) and 4 CTAs (85)
+// 4 CTAs per SM is the resident count the shared-memory footprint allows on the BASELINE
+// configurations; the register allocation is told so (measured: ptxas' unconstrained choice
+// of 56 registers spills in the slot pass and is 3 % slower).  FVM_MIN_CTAS > 0 overrides.
 #if defined(FVM_MIN_CTAS) && FVM_MIN_CTAS > 0
 extern "C" __global__ void __launch_bounds__(FVM_THREADS, FVM_MIN_CTAS)
 #else
-extern "C" __global__ void __launch_bounds__(FVM_THREADS)
+extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
 #endif
     fvm_tile_kernel(const FvmTileArgs a) {
   extern __shared__ __align__(16) unsigned char sm[];
@@ -359,40 +495,40 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < FVM_STAGES; ++i) {
-      fvm_mbar_init(full + i, 1);                    // the producer's expect_tx arrival
+      fvm_mbar_init(full + i, FVM_PRODUCERS);        // every producer warp's expect_tx arrival
       fvm_mbar_init(empty + i, FVM_CONSUMER_WARPS);  // one arrival per consumer warp
     }
+    for (int i = 0; i < FVM_PRODUCERS * FVM_NDESC; ++i)
+      fvm_mbar_init((unsigned long long*)(sm + L.dbar) + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (threadIdx.x < 32) {
-    // ===================== producer warp (one elected lane) ===================
-    if (threadIdx.x == 0) {
-      int t = blockIdx.x;
-      if (t < a.ntiles) {
-        // tile t of the walk is tile (t + tile_rot) mod ntiles of the mesh
-        auto rot = [&](int i) { return i + a.tile_rot < a.ntiles ? i + a.tile_rot : i + a.tile_rot - a.ntiles; };
-        bool halo_ready = false;
-        FvmTileDesc d = fvm_load_desc(a.tiles + rot(t));
-        for (int it = 0; t < a.ntiles; ++it) {
-          const int st = it % FVM_STAGES;
-          const int tn = t + gridDim.x;
-          FvmTileDesc dn = d;
-          if (tn < a.ntiles) dn = fvm_load_desc(a.tiles + rot(tn));  // next descriptor in flight
-          if (it >= FVM_STAGES) fvm_mbar_wait(empty + st, ((it / FVM_STAGES) - 1) & 1);
-          fvm_produce(a, L, sm + L.stage0 + st * L.stage_bytes, full + st, d, halo_ready);
-          d = dn;
-          t = tn;
-        }
-      }
+  if (threadIdx.x < 32 * FVM_PRODUCERS) {
+    // ===================== producer warps (one elected lane each) =============
+#if FVM_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#endif
+    if ((threadIdx.x & 31) == 0) {
+      const int p = threadIdx.x >> 5;
+      if (p == 0) fvm_producer_warp<0>(a, L, sm, full, empty);
+#if FVM_PRODUCERS > 1
+      else if (p == 1) fvm_producer_warp<1>(a, L, sm, full, empty);
+#endif
+#if FVM_PRODUCERS > 2
+      else if (p == 2) fvm_producer_warp<2>(a, L, sm, full, empty);
+      else fvm_producer_warp<3>(a, L, sm, full, empty);
+#endif
     }
     return;
   }
+#if FVM_SETMAXNREG
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+#endif
 
   // ========================= consumer warps ==================================
   const int lane = threadIdx.x & 31;
-  const int cw = (threadIdx.x >> 5) - 1;  // consumer warp id
+  const int cw = (threadIdx.x >> 5) - FVM_PRODUCERS;  // consumer warp id
 
   int it = 0;
   for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
@@ -460,8 +596,8 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
       // 32-slot chunks; a warp takes FVM_ILP consecutive chunks per trip and keeps their
       // (independent) load -> functor chains in flight together: with 4 math warps per
       // scheduler the pass is bound by the latency of one chain, not by issue slots.
-      // Lanes past the tile's last slot run on entry 0 of the tile (valid addresses) and
-      // store nothing.
+      // Lanes past the tile's last slot run on an all-zero metadata word (first pair, row 0,
+      // table entry 0: valid addresses, one pair) and store nothing.
 #pragma unroll 1
       for (int kb = cw * (32 * FVM_ILP) + lane; kb < d_nk + lane; kb += FVM_NCT * FVM_ILP) {
         unsigned meta[FVM_ILP];
@@ -471,7 +607,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
         for (int j = 0; j < FVM_ILP; ++j) {
           kk[j] = kb + 32 * j;
           act[j] = kk[j] < d_nk;
-          meta[j] = s_meta[act[j] ? kk[j] : 0];
+          meta[j] = act[j] ? s_meta[kk[j]] : 0u;  // 0: pair 0, one pair, row 0, table entry 0
         }
         int g[FVM_ILP], sl[FVM_ILP];
         double x00[FVM_ILP], x01[FVM_ILP], x02[FVM_ILP], u0[FVM_ILP];
@@ -628,10 +764,20 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS)
         {
           // the first shares of the row are loaded together, then added in slot order (a
           // share past the row's end reads as +0.0: exact); the loop below takes the rest
-          double vD[FVM_ROW_AHEAD], vC[FVM_ROW_AHEAD];
+#if FVM_ACC_D
+          double vD[FVM_ROW_AHEAD];
+#endif
+#if FVM_ACC_C
+          double vC[FVM_ROW_AHEAD];
+#endif
 #pragma unroll
           for (int t = 0; t < FVM_ROW_AHEAD; ++t) {
-            vD[t] = vC[t] = 0.0;
+#if FVM_ACC_D
+            vD[t] = 0.0;
+#endif
+#if FVM_ACC_C
+            vC[t] = 0.0;
+#endif
             if (b + t < e - 1) {
 #if FVM_ACC_D
               vD[t] = s_accd[b + t];

@@ -479,3 +479,93 @@ class DistributedFvm:
         """Sum of squares of the owned residual (deterministic); the caller adds
         the ranks' values with one all-reduce of a double."""
         return self.eng.norm2(self.F.ptr, self.part.n_owned) ** 2
+
+
+def parity_selfcheck(group=None, verbose=False):
+    """N-rank result == 1-rank result, bit for bit, on small meshes (structured, jittered
+    and randomly renumbered): linear assembly (no collective), residual and Jacobian
+    values through the fused peer-memory halo, several epochs.  Every rank partitions the
+    same global mesh; rank 0 gathers the owned rows and compares them with its own
+    single-GPU engine.  Returns True on every rank iff everything matched.  Used by
+    ``bench.py --gpus N`` (``"dist_parity"``) and the multi-GPU tests."""
+    import torch
+    import torch.distributed as dist
+
+    from . import form_language as fl
+    from . import meshes
+    from .problem import discretize as discretize_1gpu
+    from .problem import discretize_linear as discretize_linear_1gpu
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    import sympy
+
+    class ConvDiff:
+        def apply(self, u):
+            a = sympy.Matrix([2, 1, 0])
+            return fl.integrate(
+                lambda x: -fl.n_dot_grad(u(x)) + fl.dot(a.T, fl.n) * u(x), fl.dS
+            ) - fl.integrate(lambda x: 1.0, fl.dV)
+
+        def dirichlet(self, u):
+            return [(u, fl.Boundary())]
+
+    class Bratu:
+        def apply(self, u):
+            return fl.integrate(lambda x: -fl.n_dot_grad(u(x)), fl.dS) - fl.integrate(
+                lambda x: 2.0 * sympy.exp(u(x)), fl.dV
+            )
+
+        def dirichlet(self, u):
+            return [(u, fl.Boundary())]
+
+    def renumbered(p, c, seed):
+        perm = numpy.random.default_rng(seed).permutation(len(p))
+        inv = numpy.empty(len(p), dtype=numpy.int64)
+        inv[perm] = numpy.arange(len(p))
+        return numpy.ascontiguousarray(p[perm]), inv[c]
+
+    xs = numpy.linspace(0.0, 1.0, 97)
+    cases = []
+    p, c = meshes.jitter(*meshes.rectangle_tri(xs, xs[:71]), scale=0.2, seed=0)
+    cases.append(("rect 97x71 jittered", p, c))
+    cases.append(("rect 97x71 renumbered", *renumbered(p, c, 1)))
+    zs = numpy.linspace(0.0, 1.0, 17)
+    p, c = meshes.jitter(*meshes.cube_tetra(zs, zs, zs), scale=0.15, seed=2)
+    cases.append(("cube 17^3 jittered", p, c))
+    ok = True
+    for name, p, c in cases:
+        mesh = meshes.Mesh(p, c)
+        n = len(p)
+        part = Partition(mesh, rank, world)
+        rng = numpy.random.default_rng(5)
+        us = [0.3 * rng.standard_normal(n) for _ in range(3)]
+        dp = DistributedFvm(Bratu(), part, halo="peer", group=group)
+        Fs, Js = [], []
+        for u in us:  # three epochs: both u buffers and a buffer reuse
+            Fs.append(dp.eval(part.owned(u)).tobytes())
+            Js.append(dp.jacobian_values(part.owned(u)).data.tobytes())
+        dist.barrier(group=group)
+        dp.halo.close()
+        A, b = discretize_linear(ConvDiff(), part)
+        mine = (Fs, Js, A.data.tobytes(), A.indices.tobytes(), b.tobytes())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        if rank == 0:
+            f1, j1 = discretize_1gpu(Bratu(), mesh)
+            A1, b1 = discretize_linear_1gpu(ConvDiff(), mesh)
+            same = (
+                b"".join(g[2] for g in gathered) == A1.data.tobytes()
+                and b"".join(g[3] for g in gathered) == A1.indices.tobytes()
+                and b"".join(g[4] for g in gathered) == b1.tobytes()
+            )
+            for k, u in enumerate(us):
+                same = same and b"".join(g[0][k] for g in gathered) == f1.eval(u).tobytes()
+                same = same and (
+                    b"".join(g[1][k] for g in gathered) == j1.get_linear_operator(u).data.tobytes()
+                )
+            if verbose:
+                print(f"dist parity, {name}, {world} ranks: bit-identical={same}", flush=True)
+            ok = ok and same
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())

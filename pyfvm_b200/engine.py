@@ -53,6 +53,7 @@ class KernelOpts(ctypes.Structure):
         ("consumer_warps", c_int32),
         ("stages", c_int32),
         ("ctas_per_sm", c_int32),
+        ("producers", c_int32),
     ]
 
 
@@ -307,6 +308,7 @@ class Engine:
                 consumer_warps=functors.consumer_warps,
                 stages=functors.stages,
                 ctas_per_sm=functors.ctas_per_sm,
+                producers=functors.producers,
             )
             self._ck(
                 self.lib.fvm_kernel_create(

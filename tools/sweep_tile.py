@@ -31,7 +31,8 @@ def main():
     ap.add_argument("--modes", default="0,1")
     ap.add_argument("--variants", default="")
     ap.add_argument("--fmad", type=int, default=0)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()
     ints = lambda s: [int(x) for x in s.split(",")]
     variants = []
@@ -66,6 +67,9 @@ def main():
         vec = eng.alloc(8 * n + 16)
         R = dm.n_halfedges / 2.0
         for mode in ints(args.modes):
+            # build every variant first, then time them round-robin `reps` times: clocks and
+            # box state drift over a sweep, so variants are compared on interleaved samples
+            runs = []
             for tv in variants:
                 tune = codegen.tuning(cdim)
                 tune.update(tv)
@@ -77,7 +81,7 @@ def main():
                         dm.launch(k0, dirid=d_dir.ptr, u=u.ptr, data=data.ptr, vec=vec.ptr)
                         sysm = solvers.DeviceSystem(dm, data.ptr)
                         y = eng.alloc(8 * n + 16)
-                        run = lambda: sysm.matvec(u.ptr, y.ptr)
+                        run = lambda sysm=sysm, y=y: sysm.matvec(u.ptr, y.ptr)
                         alg = 12 * dm.nnz + 20 * n
                         info = {}
                     else:
@@ -86,7 +90,7 @@ def main():
                             lw, mode, [None] * len(lw.edge), [None] * len(lw.vertex), tune
                         )
                         k = eng.kernel(fun, fmad=bool(args.fmad))
-                        run = lambda: dm.launch(k, dirid=d_dir.ptr, u=u.ptr, data=data.ptr, vec=vec.ptr)
+                        run = lambda k=k: dm.launch(k, dirid=d_dir.ptr, u=u.ptr, data=data.ptr, vec=vec.ptr)
                         alg = bench.algorithmic_bytes(
                             R, dm.nnz, n, dim, fun.uses_x, fun.uses_el,
                             "residual" if mode == 1 else "assembly",
@@ -94,17 +98,23 @@ def main():
                         info = k.info(dm)
                     for _ in range(5):
                         run()
-                    eng.timer_begin()
-                    for _ in range(args.steps):
-                        run()
-                    ms = eng.timer_end() / args.steps
+                    eng.sync()
                 except engine.FvmError as e:
                     print(f"q={q} mode={mode} {tv}: FAILED {str(e)[:200]}", flush=True)
                     continue
+                runs.append((tv, run, alg, info, []))
+            for _ in range(args.reps):
+                for tv, run, alg, info, ms in runs:
+                    eng.timer_begin()
+                    for _ in range(args.steps):
+                        run()
+                    ms.append(eng.timer_end() / args.steps)
+            for tv, run, alg, info, ms in runs:
+                med, best = float(numpy.median(ms)), min(ms)
                 print(
-                    f"q={st['quantum']} mode={mode} {tv or 'default'}: {ms:.4f} ms  "
-                    f"{alg / ms / 1e6:.0f} GB/s alg  frac={alg / ms / 1e6 / peak:.3f}  "
-                    f"{R / ms / 1e6:.1f} Gcontrib/s  {info}",
+                    f"q={st['quantum']} mode={mode} {tv or 'default'}: median {med:.4f} ms (min {best:.4f})  "
+                    f"{alg / med / 1e6:.0f} GB/s alg  frac={alg / med / 1e6 / peak:.3f}  "
+                    f"regs={info.get('regs')} grid={info.get('grid')} smem={info.get('smem')}",
                     flush=True,
                 )
         del dm, data, vec
