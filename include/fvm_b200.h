@@ -51,6 +51,7 @@ typedef struct fvm_kernel fvm_kernel;
 #define FVM_KF_DIR 64u       /* Dirichlet conditions present                 */
 #define FVM_KF_EDGE_D 128u   /* edge functor writes a diagonal coefficient   */
 #define FVM_KF_EDGE_C 256u   /* edge functor writes an rhs / residual part   */
+#define FVM_KF_SA 512u       /* vertex functor reads boundary surface areas  */
 
 int fvm_version(void);
 const char* fvm_last_error(void);
@@ -146,6 +147,24 @@ int fvm_mesh_pattern_dev(fvm_mesh* mesh, const int32_t** indptr_dev, const int32
 int fvm_mesh_update_geometry(fvm_mesh* mesh, int64_t n_records, int32_t n_vertices,
                              const double* ce_ratios, const double* edge_len, const double* coords,
                              const double* control_volumes, int on_device);
+
+/* user-supplied numeric edge blocks (the reference's pyfvm.fvm_matrix.EdgeMatrixKernel:
+ * eval(mesh, cell_mask) returns a (2, 2, records) array instead of a symbolic integrand).
+ * diag_vals / off_vals hold 2 * n_records entries, side-major: entry h < n_records is the
+ * row-of-idx0 view of record h (block[0][0], block[0][1]), entry n_records + h the
+ * row-of-idx1 view (block[1][1], block[1][0]).  They REPLACE the mesh's ce_ratio /
+ * edge_length half-edge streams; a functor set with D = edge_ce_ratio, O = edge_length then
+ * assembles them through the same tile kernel.  The mesh must have been created with
+ * edge_len. */
+int fvm_mesh_set_halfedge_values(fvm_mesh* mesh, int64_t n_records, const double* diag_vals,
+                                 const double* off_vals, int on_device);
+/* per-vertex measure of the domain boundary (meshplex's surface_areas: the part of the
+ * boundary faces that belongs to a vertex; 0 off the boundary) -- the weight of dGamma
+ * integrals (Neumann / Robin terms), which the reference evaluates per boundary vertex like
+ * a dV term with surface_area in place of control_volume [README.md:79 "more examples"].
+ * Only needed when a functor set carries FVM_KF_SA. */
+int fvm_mesh_set_surface_areas(fvm_mesh* mesh, const double* surface_areas, int32_t n_vertices,
+                               int on_device);
 
 /* ---- mesh generation and geometry on the device (the step before the
  * path).  meshplex derives idx_hierarchy / ce_ratios / ei_dot_ei / control_volumes

@@ -24,6 +24,7 @@ from . import form_language
 from .discretize import discretize
 from .discretize_linear import discretize_linear, split
 from .discretize_linear import lower as lower_linear
+from .fvm_matrix import EdgeMatrixKernel, get_fvm_matrix
 from .linear_fvm_problem import get_linear_fvm_problem
 from .newton import newton
 
@@ -33,6 +34,8 @@ __all__ = [
     "discretize_linear",
     "lower_linear",
     "get_linear_fvm_problem",
+    "get_fvm_matrix",
+    "EdgeMatrixKernel",
     "split",
     "newton",
 ]

@@ -46,6 +46,20 @@ class VertexKernel:
         return self.val(u, control_volumes, X) + zero
 
 
+class BoundaryKernel:
+    """``dGamma`` term (see ``discretize_linear.BoundaryLinearKernel``)."""
+
+    def __init__(self, val, subdomains):
+        self.val = val
+        self.subdomains = subdomains
+
+    def eval(self, u, mesh, vertex_mask):
+        surface_areas = mesh.surface_areas[vertex_mask]
+        X = mesh.node_coords[vertex_mask].T
+        zero = numpy.zeros(len(surface_areas))
+        return self.val(u, surface_areas, X) + zero
+
+
 class DirichletKernel:
     def __init__(self, val, subdomain):
         self.val = val
@@ -180,8 +194,24 @@ def discretize(obj, mesh):
             jac_vertex_kernels.append(
                 VertexKernel(sympy.lambdify(args, sympy.diff(expr, uk0), modules=a2a), sds)
             )
+        elif isinstance(integral.measure, fl.CellSurface):
+            x = sympy.DeferredVector("x")
+            fx = integral.integrand(x)
+            uk0 = sympy.Symbol("uk0")
+            try:
+                expr = fx.subs(u(x), uk0)
+            except AttributeError:
+                expr = sympy.sympify(fx)
+            surface_area = sympy.Symbol("surface_area")
+            expr *= surface_area
+            sds = _sd_list(integral.subdomains)
+            args = (uk0, surface_area, x)
+            vertex_kernels.append(BoundaryKernel(sympy.lambdify(args, expr, modules=a2a), sds))
+            jac_vertex_kernels.append(
+                BoundaryKernel(sympy.lambdify(args, sympy.diff(expr, uk0), modules=a2a), sds)
+            )
         else:
-            raise NotImplementedError("dGamma integrals: out of scope (SURVEY §2)")
+            raise NotImplementedError(f"unknown measure {integral.measure}")
 
     dirichlets, jac_dirichlets = [], []
     dirichlet = getattr(obj, "dirichlet", None)

@@ -81,6 +81,26 @@ class VertexLinearKernel:
         )
 
 
+class BoundaryLinearKernel:
+    """``dGamma`` term: evaluated per vertex like a ``dV`` term, weighted with the vertex's
+    share of the domain boundary (``mesh.surface_areas``, 0 off the boundary)."""
+
+    def __init__(self, mesh, linear, affine, subdomains):
+        self.mesh = mesh
+        self.linear = linear
+        self.affine = affine
+        self.subdomains = subdomains
+
+    def eval(self, vertex_mask):
+        surface_areas = self.mesh.surface_areas[vertex_mask]
+        X = self.mesh.node_coords[vertex_mask].T
+        ones = numpy.ones(len(surface_areas))
+        return (
+            self.linear(surface_areas, X) * ones,
+            self.affine(surface_areas, X) * ones,
+        )
+
+
 class DirichletLinearKernel:
     def __init__(self, mesh, coeff, rhs, subdomain):
         self.mesh = mesh
@@ -154,8 +174,26 @@ def lower(obj, mesh):
             vertex_kernels.append(
                 VertexLinearKernel(mesh, l_eval, a_eval, _sd_list(integral.subdomains))
             )
+        elif isinstance(integral.measure, fl.CellSurface):
+            # dGamma: like dV with surface_area in place of control_volume
+            x = sympy.DeferredVector("x")
+            fx = integral.integrand(x)
+            uk0 = sympy.Symbol("uk0")
+            try:
+                expr = fx.subs(u(x), uk0)
+            except AttributeError:
+                expr = fx
+            surface_area = sympy.Symbol("surface_area")
+            expr *= surface_area
+            affine, linear, nonlinear = split(expr, uk0)
+            assert nonlinear == 0
+            l_eval = sympy.lambdify((surface_area, x), linear, modules=a2a)
+            a_eval = sympy.lambdify((surface_area, x), affine, modules=a2a)
+            vertex_kernels.append(
+                BoundaryLinearKernel(mesh, l_eval, a_eval, _sd_list(integral.subdomains))
+            )
         else:
-            raise NotImplementedError("dGamma integrals: out of scope (SURVEY §2)")
+            raise NotImplementedError(f"unknown measure {integral.measure}")
 
     dirichlet = getattr(obj, "dirichlet", None)
     if callable(dirichlet):

@@ -7,13 +7,17 @@ mesh) -> (f, jacobian)``, ``f.eval(u)``, ``jacobian.get_linear_operator(u0)``,
 through ``libfvm_b200.so`` (C-ABI, ``include/fvm_b200.h``); there is no CPU
 fallback.
 """
-from . import form_language
+from . import form_language, fvm_matrix
+from .fvm_matrix import EdgeMatrixKernel, get_fvm_matrix
 from .newton import newton
 from .problem import FvmProblem, Jacobian, LinearProblem, discretize, discretize_linear
 
 __version__ = "0.1.0"
 __all__ = [
     "form_language",
+    "fvm_matrix",
+    "EdgeMatrixKernel",
+    "get_fvm_matrix",
     "discretize",
     "discretize_linear",
     "newton",

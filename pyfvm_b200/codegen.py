@@ -17,7 +17,7 @@ MODE_LINEAR, MODE_RESIDUAL, MODE_JACOBIAN = 0, 1, 2
 
 # FVM_F_* bits of csrc/fvm_tile_args.h (= FVM_KF_* of include/fvm_b200.h)
 F_EDGE_EL, F_EDGE_MASK, F_X, F_U, F_CV, F_VMASK, F_DIR = 1, 2, 4, 8, 16, 32, 64
-F_EDGE_D, F_EDGE_C = 128, 256
+F_EDGE_D, F_EDGE_C, F_SA = 128, 256, 512
 
 
 def tuning(cell_dim=2):
@@ -161,6 +161,7 @@ class Functors:
     vert_masked: bool
     has_dirichlet: bool
     needs_u: bool
+    uses_sa: bool = False
 
 
 def generate(lowered, mode, edge_bits, vert_bits, tune=None):
@@ -185,6 +186,7 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
     flags |= F_X if (edge_x or vert_x) else 0
     flags |= F_U if (edge_u or vert_u) else 0
     flags |= F_CV if _uses(flat_v, [lo.CV]) else 0
+    flags |= F_SA if _uses(flat_v, [lo.SA]) else 0
     flags |= F_VMASK if any(b is not None for b in vert_bits) else 0
     flags |= F_DIR if lowered.dirichlet else 0
     # which row sums the edge functor feeds in this mode (their per-slot shares
@@ -244,7 +246,8 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
     L.append("")
     L.append(
         "__device__ __forceinline__ void fvm_vertex(const double uk0, const double control_volume,\n"
-        "    const double x_0, const double x_1, const double x_2, const unsigned mask,\n"
+        "    const double surface_area, const double x_0, const double x_1, const double x_2,\n"
+        "    const unsigned mask,\n"
         "    double& L, double& C) {"
     )
     done = set()
@@ -254,6 +257,7 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
     L.append("")
     L.append(
         "__device__ __forceinline__ void fvm_dirichlet(const int id, const double uk0,\n"
+        "    const double control_volume, const double surface_area,\n"
         "    const double x_0, const double x_1, const double x_2,\n"
         "    double& coeff, double& val) {"
     )
@@ -282,4 +286,5 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         vert_masked=bool(flags & F_VMASK),
         has_dirichlet=bool(flags & F_DIR),
         needs_u=bool(flags & F_U),
+        uses_sa=bool(flags & F_SA),
     )

@@ -74,7 +74,7 @@ struct FvmSmemLayout {
   unsigned dbar, ring;  // per producer warp: FVM_NDESC mbarriers / 128-byte descriptor slots
   // within a stage (accd / accc: per-slot diagonal / rhs contributions waiting for
   // the row fold; dg: offset of the diagonal slot inside every row)
-  unsigned desc, ce, el, mask, meta, rowptr, cv, xy, u, dir, vmask, accd, accc, dg, mat;
+  unsigned desc, ce, el, mask, meta, rowptr, cv, sa, xy, u, dir, vmask, accd, accc, dg, mat;
   unsigned total;
 };
 
@@ -89,6 +89,7 @@ struct FvmTileArgs {
   const unsigned char* he_mask;    // [H] edge-term subdomain bits (or null)
   const double* coords;            // [nverts*xs] vertex coordinates, xs = 2 (dim 2) or 4 (dim 3)
   const double* cv;                // [nverts] control volumes
+  const double* sa;                // [nverts] boundary surface areas (dGamma terms; or null)
   const unsigned char* vmask;      // [nverts] vertex-term subdomain bits (or null)
   const unsigned char* dir_id;     // [nverts] 0 = free, k = Dirichlet term k-1 wins (or null)
   const double* u;                 // [nverts] state (residual / Jacobian modes), x (SpMV)
@@ -129,6 +130,7 @@ struct FvmTileArgs {
 #define FVM_F_DIR 64u       // Dirichlet conditions present
 #define FVM_F_EDGE_D 128u   // edge functor writes D (diagonal coefficient) in this mode
 #define FVM_F_EDGE_C 256u   // edge functor writes C (rhs / residual part) in this mode
+#define FVM_F_SA 512u       // vertex functor reads boundary surface areas (dGamma terms)
 
 #ifdef __CUDACC__
 #define FVM_HD __host__ __device__
@@ -157,6 +159,7 @@ FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_r
   L.meta = o;   o += fvm_round16(sl * 4u) + 16u;
   L.rowptr = o; o += fvm_round16((nr + 1u) * 4u) + 16u;
   L.cv = o;     o += (flags & FVM_F_CV) ? fvm_round16(nr * 8u) + 16u : 0u;
+  L.sa = o;     o += (flags & FVM_F_SA) ? fvm_round16(nr * 8u) + 16u : 0u;
   L.xy = o;     o += (flags & FVM_F_X) ? fvm_round16(xt * 8u * fvm_coord_stride(dim)) : 0u;
   L.u = o;      o += (flags & FVM_F_U) ? fvm_round16(xt * 8u) : 0u;
   L.dir = o;    o += (flags & FVM_F_DIR) ? fvm_round16(nr) + 16u : 0u;

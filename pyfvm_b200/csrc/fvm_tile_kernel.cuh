@@ -13,8 +13,8 @@
 //   FVM_EDGE_USES_X / _U, FVM_VERT_USES_X / _U, FVM_HAS_VERTEX, FVM_EDGE_FACTORED
 // and the three sympy-printed device functors
 //   fvm_edge(uk0, uk1, x0_0..2, x1_0..2, edge_ce_ratio, edge_length, mask, &D, &O, &C)
-//   fvm_vertex(uk0, control_volume, x_0..2, mask, &L, &C)
-//   fvm_dirichlet(id, uk0, x_0..2, &coeff, &val)
+//   fvm_vertex(uk0, control_volume, surface_area, x_0..2, mask, &L, &C)
+//   fvm_dirichlet(id, uk0, control_volume, surface_area, x_0..2, &coeff, &val)
 // (edge functor outputs per half-edge (row, col): D -> slot (row,row),
 //  O -> slot (row,col), C -> rhs/residual of row).
 //
@@ -58,6 +58,7 @@
 #define FVM_STAGE_X ((FVM_FLAGS & FVM_F_X) != 0)
 #define FVM_STAGE_U ((FVM_FLAGS & FVM_F_U) != 0)
 #define FVM_STAGE_CV ((FVM_FLAGS & FVM_F_CV) != 0)
+#define FVM_STAGE_SA ((FVM_FLAGS & FVM_F_SA) != 0)
 #define FVM_VERT_MASKED ((FVM_FLAGS & FVM_F_VMASK) != 0)
 #define FVM_HAS_DIRICHLET ((FVM_FLAGS & FVM_F_DIR) != 0)
 
@@ -257,6 +258,10 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
   const FvmStage g_cv = fvm_stage(a.cv + v0, (unsigned)d_nr * 8u);
   if (FVM_ROLE_MINE(1, P_ID)) total += g_cv.bytes;
 #endif
+#if FVM_STAGE_SA
+  const FvmStage g_sa = fvm_stage(a.sa + v0, (unsigned)d_nr * 8u);
+  if (FVM_ROLE_MINE(1, P_ID)) total += g_sa.bytes;
+#endif
 #if FVM_STAGE_X
   if (FVM_ROLE_MINE(2, P_ID)) total += n_tab * 8u * FVM_XS;
 #endif
@@ -317,6 +322,9 @@ __device__ __forceinline__ void fvm_produce(const FvmTileArgs& a, const FvmSmemL
     fvm_bulk_g2s(stage + L.rowptr, g_rp.src, g_rp.bytes, full);
 #if FVM_STAGE_CV
     if (g_cv.bytes) fvm_bulk_g2s(stage + L.cv, g_cv.src, g_cv.bytes, full);
+#endif
+#if FVM_STAGE_SA
+    if (g_sa.bytes) fvm_bulk_g2s(stage + L.sa, g_sa.src, g_sa.bytes, full);
 #endif
 #if FVM_HAS_DIRICHLET
     if (g_dir.bytes) fvm_bulk_g2s(stage + L.dir, g_dir.src, g_dir.bytes, full);
@@ -568,6 +576,9 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
 #if FVM_STAGE_CV
     const double* s_cv = (const double*)(stage + L.cv + fvm_shift_at(v0, 8u));
 #endif
+#if FVM_STAGE_SA
+    const double* s_sa = (const double*)(stage + L.sa + fvm_shift_at(v0, 8u));
+#endif
 #if FVM_STAGE_X
     const double* s_xy = (const double*)(stage + L.xy);
 #endif
@@ -808,7 +819,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
           sC += s_accc[k];
 #endif
         }
-        double x00 = 0.0, x01 = 0.0, x02 = 0.0, u0 = 0.0, cvv = 0.0;
+        double x00 = 0.0, x01 = 0.0, x02 = 0.0, u0 = 0.0, cvv = 0.0, sav = 0.0;
 #if FVM_STAGE_X && (FVM_VERT_USES_X)
         {
           const double2 q0 = *(const double2*)(s_xy + FVM_XS * (xoff + g));
@@ -825,6 +836,9 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
 #if FVM_STAGE_CV
         cvv = s_cv[g];
 #endif
+#if FVM_STAGE_SA
+        sav = s_sa[g];
+#endif
 #if FVM_MODE == FVM_MODE_SPMV
         sC += s_mat[b + (int)s_dg[g]] * u0;  // the diagonal entry closes the row
 #endif
@@ -835,7 +849,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
           vm = s_vm[g];
 #endif
           double VL = 0.0, VC = 0.0;
-          fvm_vertex(u0, cvv, x00, x01, x02, vm, VL, VC);
+          fvm_vertex(u0, cvv, sav, x00, x01, x02, vm, VL, VC);
           sD += VL;
           sC += VC;
         }
@@ -849,7 +863,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
         const int dir = s_dir[g];
         if (dir) {
           double dc = 0.0, dv = 0.0;
-          fvm_dirichlet(dir, u0, x00, x01, x02, dc, dv);
+          fvm_dirichlet(dir, u0, cvv, sav, x00, x01, x02, dc, dv);
           sD = dc;       // row := coeff * e_row
           out_vec = dv;  // rhs := -affine (linear) / F := condition(u) (residual)
 #if FVM_MODE == FVM_MODE_LINEAR || FVM_MODE == FVM_MODE_JACOBIAN

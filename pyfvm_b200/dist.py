@@ -41,7 +41,8 @@ class LocalMesh:
     masks" are per record."""
 
     def __init__(self, points, idx, ce, ei_dot_ei, cv, boundary, rec_global, cell_of_record,
-                 parent):
+                 parent, verts=None):
+        self._verts = verts
         self.points = points
         nc = numpy.zeros((len(points), 3))
         nc[:, : points.shape[1]] = points
@@ -55,6 +56,11 @@ class LocalMesh:
         self._cell_of_record = cell_of_record
         self._parent = parent
         self.cell_dim = getattr(parent, "cell_dim", 3 if numpy.asarray(parent.idx_hierarchy).ndim == 4 else 2)
+
+    @property
+    def surface_areas(self):
+        """The GLOBAL boundary measure of the local vertices (dGamma terms)."""
+        return numpy.asarray(self._parent.surface_areas)[self._verts]
 
     def get_vertex_mask(self, subdomain=None):
         if subdomain is None:
@@ -108,6 +114,7 @@ class Partition:
             rec_global=rec,
             cell_of_record=cell_of_record,
             parent=mesh,
+            verts=verts,
         )
         # ---- halo plan -------------------------------------------------------
         # receive: ghosts sorted by global id are grouped by owner (owners are

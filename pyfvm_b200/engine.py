@@ -92,6 +92,8 @@ SYMBOLS = {
     "fvm_mesh_update_geometry": (
         c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int],
     ),
+    "fvm_mesh_set_surface_areas": (c_int, [c_void_p, c_void_p, c_int32, c_int]),
+    "fvm_mesh_set_halfedge_values": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int]),
     "fvm_gen_rectangle_tri": (
         c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     ),
@@ -448,6 +450,7 @@ class DeviceMesh:
             ms.value,
         )
         self._pattern = None
+        self.has_sa = False
         self.shared = False  # True while other problems may hold this object (mesh cache)
 
     TILE_DTYPE = numpy.dtype(
@@ -503,6 +506,24 @@ class DeviceMesh:
             )
             self._pattern = (indptr, indices)
         return self._pattern
+
+    def set_halfedge_values(self, diag_vals, off_vals):
+        """Replace the ce_ratio / edge_length streams with user-evaluated edge blocks (2R
+        entries each, side-major; see ``fvm_mesh_set_halfedge_values``)."""
+        d = numpy.ascontiguousarray(diag_vals, dtype=numpy.float64).reshape(-1)
+        o = numpy.ascontiguousarray(off_vals, dtype=numpy.float64).reshape(-1)
+        assert d.size == o.size == 2 * self.R
+        assert not self.shared, "the streams of a cached device mesh must not be overwritten"
+        self.eng._ck(
+            self.eng.lib.fvm_mesh_set_halfedge_values(self.handle, self.R, _ptr(d), _ptr(o), 0)
+        )
+
+    def set_surface_areas(self, sa):
+        """Per-vertex boundary measure (``mesh.surface_areas``): the weight of dGamma terms."""
+        sa = numpy.ascontiguousarray(sa, dtype=numpy.float64)
+        assert sa.shape == (self.n,)
+        self.eng._ck(self.eng.lib.fvm_mesh_set_surface_areas(self.handle, _ptr(sa), self.n, 0))
+        self.has_sa = True
 
     def update_geometry(self, ce=None, el=None, coords=None, cv=None):
         """Re-upload per-record / per-vertex geometry of the same connectivity

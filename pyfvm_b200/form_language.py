@@ -40,7 +40,8 @@ class ControlVolumeSurface(Measure):
 
 
 class CellSurface(Measure):
-    """``dGamma``: domain boundary faces (not lowered yet)."""
+    """``dGamma``: the domain boundary (Neumann / Robin terms) -> evaluated per boundary
+    vertex with ``mesh.surface_areas`` as the weight (vertex functor)."""
 
 
 dV = ControlVolume()

@@ -24,6 +24,7 @@ UK1 = sympy.Symbol("uk1")
 CE = sympy.Symbol("edge_ce_ratio")
 EL = sympy.Symbol("edge_length")
 CV = sympy.Symbol("control_volume")
+SA = sympy.Symbol("surface_area")
 X0 = [sympy.Symbol(f"x0_{k}") for k in range(3)]
 X1 = [sympy.Symbol(f"x1_{k}") for k in range(3)]
 XV = [sympy.Symbol(f"x_{k}") for k in range(3)]
@@ -123,6 +124,18 @@ def lower_vertex_integrand(integrand, u, dim):
     return _flatten_dim(expr * CV, dim)
 
 
+def lower_face_integrand(integrand, u, dim):
+    """``dGamma``: a boundary integral is evaluated per boundary vertex like a ``dV`` term,
+    weighted with the vertex's share of the domain boundary (``mesh.surface_areas``)
+    instead of its control volume: ``integrand(x)`` with ``u(x) -> uk0``, times
+    ``surface_area`` (0 off the boundary).  Neumann and Robin conditions."""
+    fx = sympy.sympify(integrand(_x))
+    if fx.atoms(fl.n_dot_grad) or fx.atoms(fl.n_dot):
+        raise NotImplementedError("n / n_dot_grad inside a dGamma integrand (give the flux itself)")
+    expr = fx.subs(u(_x), UK0).subs(dict(zip(_XSYM, XV)), simultaneous=True)
+    return _flatten_dim(expr * SA, dim)
+
+
 def lower_dirichlet(f, u, dim):
     fx = sympy.sympify(f(_x))
     expr = fx.subs(u(_x), UK0).subs(dict(zip(_XSYM, XV)), simultaneous=True)
@@ -164,11 +177,12 @@ def _subdomain_list(subdomains):
     return list(subdomains) if subdomains else [None]
 
 
-def _check_supported(measure):
-    if isinstance(measure, fl.CellSurface):
-        raise NotImplementedError(
-            "dGamma (boundary-face) integrals are not lowered yet (SURVEY §8f rank 3)"
-        )
+def _vertex_expr(integral, u, dim):
+    """Per-vertex expression of a ``dV`` (control volume) or ``dGamma`` (boundary surface)
+    integral; both end up in the vertex functor."""
+    if isinstance(integral.measure, fl.CellSurface):
+        return lower_face_integrand(integral.integrand, u, dim)
+    return lower_vertex_integrand(integral.integrand, u, dim)
 
 
 def lower_linear(obj, dim):
@@ -179,7 +193,6 @@ def lower_linear(obj, dim):
     res = obj.apply(u)
     out = Lowered("linear", dim)
     for integral in res.integrals:
-        _check_supported(integral.measure)
         if isinstance(integral.measure, fl.ControlVolumeSurface):
             expr = lower_edge_integrand(integral.integrand, u, dim)
             affine, linear, nonlinear = split(expr, [UK0, UK1])
@@ -189,9 +202,9 @@ def lower_linear(obj, dim):
                     EdgeTerm({"diag": linear[0], "off": linear[1], "aff": affine}, sd)
                 )
         else:
-            expr = lower_vertex_integrand(integral.integrand, u, dim)
+            expr = _vertex_expr(integral, u, dim)
             affine, linear, nonlinear = split(expr, UK0)
-            assert nonlinear == 0, f"dV integrand is not linear in u: {nonlinear}"
+            assert nonlinear == 0, f"dV / dGamma integrand is not linear in u: {nonlinear}"
             for sd in _subdomain_list(integral.subdomains):
                 out.vertex.append(VertexTerm({"lin": linear, "aff": affine}, sd))
     dirichlet = getattr(obj, "dirichlet", None)
@@ -211,7 +224,6 @@ def lower_nonlinear(obj, dim):
     res = obj.apply(u)
     out = Lowered("nonlinear", dim)
     for integral in res.integrals:
-        _check_supported(integral.measure)
         if isinstance(integral.measure, fl.ControlVolumeSurface):
             expr = lower_edge_integrand(integral.integrand, u, dim)
             outs = {
@@ -222,7 +234,7 @@ def lower_nonlinear(obj, dim):
             for sd in _subdomain_list(integral.subdomains):
                 out.edge.append(EdgeTerm(outs, sd))
         else:
-            expr = lower_vertex_integrand(integral.integrand, u, dim)
+            expr = _vertex_expr(integral, u, dim)
             outs = {"val": expr, "lin": sympy.diff(expr, UK0)}
             for sd in _subdomain_list(integral.subdomains):
                 out.vertex.append(VertexTerm(outs, sd))

@@ -36,6 +36,7 @@ class Mesh:
         self._geom = None
         self._boundary = None
         self._cv = None
+        self._sa = None
 
     # -- index hierarchy ----------------------------------------------------
     @property
@@ -157,6 +158,40 @@ class Mesh:
                 kb = kb // n
             self._boundary = mask
         return self._boundary
+
+    @property
+    def surface_areas(self):
+        """Per-vertex measure of the domain boundary (meshplex's ``surface_areas``): every
+        boundary facet is split among its vertices -- a boundary edge of a triangle mesh
+        gives half its length to each endpoint, a boundary triangle of a tetrahedral mesh
+        its 2-D control-volume shares (``|e|^2 cot / 8`` per edge and endpoint).  The weight
+        of ``dGamma`` integrals; 0 for interior vertices."""
+        if self._sa is None:
+            c, d, n = self.cells_points, self.cell_dim, len(self.points)
+            facets = numpy.concatenate([numpy.delete(c, k, axis=1) for k in range(d + 1)], axis=0)
+            srt = numpy.sort(facets, axis=1)
+            key = srt[:, 0].astype(numpy.int64)
+            for k in range(1, d):
+                key = key * n + srt[:, k]
+            _, inverse, counts = numpy.unique(key, return_inverse=True, return_counts=True)
+            bf = facets[counts[inverse] == 1]  # facets that belong to exactly one cell
+            P = self.node_coords
+            sa = numpy.zeros(n)
+            if d == 2:
+                half = 0.5 * numpy.sqrt(((P[bf[:, 1]] - P[bf[:, 0]]) ** 2).sum(axis=1))
+                numpy.add.at(sa, bf[:, 0], half)
+                numpy.add.at(sa, bf[:, 1], half)
+            else:
+                p = [P[bf[:, k]] for k in range(3)]
+                e = [p[(k + 2) % 3] - p[(k + 1) % 3] for k in range(3)]  # edge k opposite vertex k
+                area2 = numpy.sqrt((numpy.cross(e[0], e[1]) ** 2).sum(axis=1))  # 2 * face area
+                for k in range(3):
+                    cot = -(e[(k + 1) % 3] * e[(k + 2) % 3]).sum(axis=1) / area2
+                    share = (e[k] ** 2).sum(axis=1) * cot / 8.0
+                    numpy.add.at(sa, bf[:, (k + 1) % 3], share)
+                    numpy.add.at(sa, bf[:, (k + 2) % 3], share)
+            self._sa = sa
+        return self._sa
 
     # -- output ---------------------------------------------------------------
     def write(self, filename, point_data=None):

@@ -96,6 +96,12 @@ class _DeviceProblem:
         self.dmesh = device_mesh(
             eng, mesh, rec_mask=rec_mask, need_el=need_el, row_range=row_range
         )
+        if any(f.uses_sa for f in self.functors.values()) and not self.dmesh.has_sa:
+            if not hasattr(mesh, "surface_areas"):
+                raise NotImplementedError(
+                    "dGamma terms need mesh.surface_areas (the per-vertex boundary measure)"
+                )
+            self.dmesh.set_surface_areas(mesh.surface_areas)
         self.n_rows = self.dmesh.n_rows
         self.kernels = {m: eng.kernel(f, fmad=fmad) for m, f in self.functors.items()}
         # (+16: the kernel's 16-byte-rounded bulk copies may read past the last element)

@@ -125,6 +125,55 @@ def subdomain_problem(fl):
     return Sub()
 
 
+def robin(fl):
+    """Poisson with a Robin condition on the whole boundary (a dGamma term, SURVEY §8f
+    rank 3) and a Dirichlet condition on the left side."""
+    lb = LeftBoundary()
+
+    class Robin:
+        def apply(self, u):
+            return (
+                fl.integrate(lambda x: -fl.n_dot_grad(u(x)), fl.dS)
+                + fl.integrate(lambda x: 2.0 * u(x) - sympy.cos(x[0]), fl.dGamma)
+                - fl.integrate(lambda x: 1.0 + x[1], fl.dV)
+            )
+
+        def dirichlet(self, u):
+            return [(lambda x: u(x) - 1.0, lb)]
+
+    return Robin()
+
+
+def neumann_only(fl):
+    """Pure Neumann data (an affine dGamma term) restricted to a boundary subdomain, plus
+    a reaction term that keeps the system regular; no Dirichlet rows at all."""
+    lb = LeftBoundary()
+
+    class Neumann:
+        def apply(self, u):
+            return (
+                fl.integrate(lambda x: -fl.n_dot_grad(u(x)), fl.dS)
+                + fl.integrate(lambda x: u(x), fl.dV)
+                - fl.integrate(lambda x: 3.0 + x[1], fl.dGamma, subdomains=[lb])
+            )
+
+    return Neumann()
+
+
+def radiation(fl):
+    """Nonlinear boundary term (u^4-type radiation) for discretize / Newton."""
+
+    class Radiation:
+        def apply(self, u):
+            return (
+                fl.integrate(lambda x: -fl.n_dot_grad(u(x)), fl.dS)
+                + fl.integrate(lambda x: 0.5 * u(x) ** 4 - sympy.exp(-x[0]), fl.dGamma)
+                + fl.integrate(lambda x: u(x) - 1.0, fl.dV)
+            )
+
+    return Radiation()
+
+
 def rectangle(nx, ny, lx=2.0, ly=1.0):
     from pyfvm_b200 import meshes
 

@@ -53,6 +53,24 @@ def manufactured(fl, dim, kind):
     return P()
 
 
+def manufactured_robin(fl):
+    """-lap(u) = f on the unit square with the ROBIN condition du/dn + u = g on the whole
+    boundary (a dGamma term, no Dirichlet rows); u = sin(pi x) sin(pi y), for which
+    g = -pi (sin(pi x) + sin(pi y)) on every side."""
+
+    class P:
+        def apply(self, u):
+            return (
+                fl.integrate(lambda x: -fl.n_dot_grad(u(x)), fl.dS)
+                + fl.integrate(
+                    lambda x: u(x) + PI * (sympy.sin(PI * x[0]) + sympy.sin(PI * x[1])), fl.dGamma
+                )
+                - fl.integrate(lambda x: 2 * PI**2 * _exact(2)(x), fl.dV)
+            )
+
+    return P()
+
+
 def _mesh(dim, n):
     from pyfvm_b200 import meshes
 
@@ -66,7 +84,8 @@ def _orders(discretize_linear, fl, dim, kind, sizes):
     errs2, errsi, hs = [], [], []
     for n in sizes:
         mesh = _mesh(dim, n)
-        A, b = discretize_linear(manufactured(fl, dim, kind), mesh)
+        prob = manufactured_robin(fl) if kind == "robin" else manufactured(fl, dim, kind)
+        A, b = discretize_linear(prob, mesh)
         u = linalg.spsolve(A.tocsc(), b)
         X = mesh.node_coords.T
         exact = numpy.prod(numpy.sin(numpy.pi * X[:dim]), axis=0)
@@ -79,7 +98,7 @@ def _orders(discretize_linear, fl, dim, kind, sizes):
     return o2, oi, errs2
 
 
-@pytest.mark.parametrize("kind", ["poisson", "convection", "reaction"])
+@pytest.mark.parametrize("kind", ["poisson", "convection", "reaction", "robin"])
 def test_oracle_second_order_2d(kind):
     import oracle
 
@@ -99,7 +118,7 @@ def test_oracle_second_order_3d():
 @pytest.mark.parametrize(
     "dim,kind,sizes",
     [(2, "poisson", [17, 33, 65, 129]), (2, "convection", [17, 33, 65, 129]),
-     (2, "reaction", [17, 33, 65]), (3, "poisson", [5, 9, 17, 33])],
+     (2, "reaction", [17, 33, 65]), (3, "poisson", [5, 9, 17, 33]), (2, "robin", [17, 33, 65])],
 )
 def test_engine_second_order(dim, kind, sizes):
     import pyfvm_b200 as eng

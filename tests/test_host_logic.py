@@ -41,11 +41,12 @@ def emulate_linear(lowered, mesh):
             cols += [a, b]
             vals += [_lam(t.outputs["diag"], eargs)(*args), _lam(t.outputs["off"], eargs)(*args)]
             numpy.subtract.at(rhs, a, _lam(t.outputs["aff"], eargs)(*args))
-    vargs = lo.XV + [lo.CV]
+    vargs = lo.XV + [lo.CV, lo.SA]
     allv = numpy.arange(n)
     for t in lowered.vertex:
         m = allv if t.subdomain is None else allv[mesh.get_vertex_mask(t.subdomain)]
-        args = [X[m, k] for k in range(3)] + [numpy.asarray(mesh.control_volumes)[m]]
+        args = [X[m, k] for k in range(3)] + [numpy.asarray(mesh.control_volumes)[m],
+                                              numpy.asarray(mesh.surface_areas)[m]]
         rows.append(m)
         cols.append(m)
         vals.append(_lam(t.outputs["lin"], vargs)(*args))
@@ -68,7 +69,8 @@ def emulate_linear(lowered, mesh):
 @pytest.mark.parametrize(
     "name,kind,args",
     [("poisson", "rect", (9, 6)), ("convection_diffusion", "rect", (8, 7)), ("reaction_x", "rect", (7, 9)),
-     ("subdomain_problem", "rect", (11, 7)), ("reaction_x", "cube", (4,))],
+     ("subdomain_problem", "rect", (11, 7)), ("reaction_x", "cube", (4,)),
+     ("robin", "rect", (9, 7)), ("robin", "cube", (5,)), ("neumann_only", "rect", (8, 6))],
 )
 def test_lowering_in_half_edge_semantics_matches_oracle(name, kind, args):
     import oracle
