@@ -113,12 +113,14 @@ typedef struct fvm_mesh_desc {
   const double* edge_len;   /* [n_records] sqrt(ei_dot_ei), may be NULL         */
   const uint8_t* rec_mask;  /* [n_records] edge-term subdomain bits, may be NULL
                                (records with mask 0 are left out of the pattern) */
-  const double* coords;     /* [n_vertices*dim] row-major                       */
+  const double* coords;     /* [n_vertices*coord_cols] row-major (first dim columns used) */
   const double* control_volumes; /* [n_vertices]; NULL: derived on the device for the
                                owned rows (needs edge_len), as sum |e|^2 ce / (2 cell_dim) */
   int32_t tile_quantum; /* 0 = default; half-edges+slots per tile              */
   int32_t cell_dim;     /* 2 triangles, 3 tetrahedra (default tile size; scale of the
                            control volumes derived when control_volumes == NULL)       */
+  int32_t coord_cols;   /* columns per vertex of the coords array, >= dim (0 = dim): a
+                           planar mesh carried with 3 columns needs no sliced host copy */
 } fvm_mesh_desc;
 
 int fvm_mesh_create(fvm_ctx* ctx, const fvm_mesh_desc* desc, fvm_mesh** out);
@@ -205,6 +207,11 @@ typedef struct fvm_kernel_opts {
 int fvm_kernel_create(fvm_ctx* ctx, const char* functor_src, const fvm_kernel_opts* opts,
                       fvm_kernel** out);
 int fvm_kernel_destroy(fvm_kernel* k);
+/* Compiled cubins are kept under $FVM_CACHE_DIR (default ~/.cache/fvm_b200; "off"
+ * disables), keyed by SHA-256 of the full translation unit + compile options + NVRTC
+ * version: a functor set is compiled once per machine, not once per process.  Counters of
+ * this process: NVRTC compilations run, cubins taken from the cache. */
+int fvm_kernel_cache_stats(int* nvrtc_compiles, int* cubin_cache_hits);
 /* registers/thread, static smem, max threads/block of the compiled entry */
 int fvm_kernel_info(fvm_kernel* k, int* regs, int* static_smem, int* max_threads);
 /* launch shape the kernel would use on this mesh: grid, block, dynamic smem bytes */
@@ -279,6 +286,14 @@ int fvm_ipc_close(fvm_ctx* ctx, void* ptr_dev);
  * system-scope release) *peer_flag_dev = epoch.  peer_flag_dev may be NULL. */
 int fvm_halo_push(fvm_ctx* ctx, const double* src_dev, const int32_t* send_index_dev, int64_t n,
                   double* peer_dst_dev, uint64_t* peer_flag_dev, uint64_t epoch);
+/* the whole exchange in ONE launch: peers_dev is a device array of n_peers records
+ *   { const int32_t* send_index_dev; double* peer_dst_dev[2]; uint64_t* peer_flag_dev; int64_t n; }
+ * (40 bytes each; peer_dst_dev[b] = the peer's ghost slots in its u buffer b); values are
+ * read from src_dev (this rank's u buffer `buffer`), and the last block of a peer to finish
+ * releases `epoch` into that peer's flag.  max_n = the longest send list; counters_dev:
+ * n_peers zero-initialised uint32 (re-armed by the kernel). */
+int fvm_halo_push_all(fvm_ctx* ctx, const void* peers_dev, int n_peers, int64_t max_n,
+                      const double* src_dev, int buffer, uint64_t epoch, uint32_t* counters_dev);
 /* stream-ordered wait until every flags_dev[i] (device array of n_flags device
  * pointers) has reached epoch; after timeout_s seconds sets *timed_out_dev = 1 and
  * returns instead of hanging. */
@@ -294,6 +309,14 @@ int fvm_assemble_halo(fvm_mesh* mesh, fvm_kernel* k, const uint8_t* vmask_dev,
                       const uint8_t* dirid_dev, const double* u_dev, double* data_dev,
                       double* vec_dev, const uint64_t* const* flags_dev, int n_flags, uint64_t epoch,
                       int32_t* timed_out_dev);
+/* fvm_halo_push_all + fvm_assemble_halo in one call: push this rank's boundary values of
+ * u_dev (its u buffer `buffer`) to every neighbour, then launch the tile kernel that waits
+ * for theirs only where a tile needs them. */
+int fvm_halo_step(fvm_mesh* mesh, fvm_kernel* k, const uint8_t* vmask_dev, const uint8_t* dirid_dev,
+                  const double* u_dev, double* data_dev, double* vec_dev,
+                  const uint64_t* const* flags_dev, int n_flags, uint64_t epoch,
+                  int32_t* timed_out_dev, const void* peers_dev, int n_peers, int64_t max_n,
+                  int buffer, uint32_t* counters_dev);
 /* y += a*x (Newton update on the device) */
 int fvm_axpy(fvm_ctx* ctx, double a, const double* x_dev, double* y_dev, int64_t n);
 

@@ -73,7 +73,8 @@ struct FvmSmemLayout {
   unsigned bar, stage0, stage_bytes;
   unsigned dbar, ring;  // per producer warp: FVM_NDESC mbarriers / 128-byte descriptor slots
   // within a stage (accd / accc: per-slot diagonal / rhs contributions waiting for
-  // the row fold; dg: offset of the diagonal slot inside every row)
+  // the row fold -- SpMV parks its products in place, over `mat`; dg: offset of the
+  // diagonal slot inside every row)
   unsigned desc, ce, el, mask, meta, rowptr, cv, sa, xy, u, dir, vmask, accd, accc, dg, mat;
   unsigned total;
 };
@@ -165,8 +166,8 @@ FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_r
   L.dir = o;    o += (flags & FVM_F_DIR) ? fvm_round16(nr) + 16u : 0u;
   L.vmask = o;  o += (flags & FVM_F_VMASK) ? fvm_round16(nr) + 16u : 0u;
   const unsigned csl = (unsigned)max_csr_slots;  // parked shares keep the CSR row stride
-  L.accd = o;   o += (flags & FVM_F_EDGE_D) ? fvm_round16(csl * 8u) : 0u;
-  L.accc = o;   o += (flags & FVM_F_EDGE_C) ? fvm_round16(csl * 8u) : 0u;
+  L.accd = o;   o += ((flags & FVM_F_EDGE_D) && mode != FVM_MODE_SPMV) ? fvm_round16(csl * 8u) : 0u;
+  L.accc = o;   o += ((flags & FVM_F_EDGE_C) && mode != FVM_MODE_SPMV) ? fvm_round16(csl * 8u) : 0u;
   L.dg = o;     o += (mode != FVM_MODE_RESIDUAL) ? fvm_round16(nr * 2u) + 16u : 0u;
   L.mat = o;    o += (mode == FVM_MODE_SPMV) ? fvm_round16((unsigned)max_csr_slots * 8u) + 16u : 0u;
   L.stage_bytes = o;

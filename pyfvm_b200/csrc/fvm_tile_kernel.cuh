@@ -591,10 +591,10 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
 #if FVM_VERT_MASKED
     const unsigned char* s_vm = stage + L.vmask + fvm_shift_at(v0, 1u);
 #endif
-#if FVM_ACC_D
+#if FVM_ACC_D && FVM_MODE != FVM_MODE_SPMV
     double* s_accd = (double*)(stage + L.accd);  // lives and dies with the stage
 #endif
-#if FVM_ACC_C
+#if FVM_ACC_C && FVM_MODE != FVM_MODE_SPMV
     double* s_accc = (double*)(stage + L.accc);
 #endif
 #if FVM_MODE != FVM_MODE_RESIDUAL
@@ -751,14 +751,21 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
 #if FVM_MODE == FVM_MODE_LINEAR || FVM_MODE == FVM_MODE_JACOBIAN
             a.data[d_s0 + sl[j]] = aO;  // consecutive lanes, (nearly) consecutive slots: coalesced
 #endif
+#if FVM_MODE == FVM_MODE_SPMV
+            // SpMV: the product is parked in place, over the slot's own (now dead) CSR value
+            ((double*)s_mat)[sl[j]] = aC;
+#else
             // parked at k + g: a row's shares stay contiguous and the row stride is the CSR
             // row length (4 + 1 / 8 + 1 on the zigzag triangle grid: odd, so the row pass
-            // below reads conflict-free; the compact stride 4 / 8 would 4-way conflict)
+            // below reads conflict-free; the compact stride 4 / 8 would 4-way conflict).
+            // (Parking in place over the slot's first ce pair was measured: the row pass then
+            // gathers through slot_meta with 4-way conflicts, 30 % slower overall.)
 #if FVM_ACC_D
             s_accd[kk[j] + g[j]] = aD;
 #endif
 #if FVM_ACC_C
             s_accc[kk[j] + g[j]] = aC;
+#endif
 #endif
           }
         }
@@ -770,25 +777,37 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
       for (int g = g_first + lane; g < g_end; g += g_step) {
         const int b = s_rp[g] - d_s0, e = s_rp[g + 1] - d_s0;  // CSR slots of the row
         double sD = 0.0, sC = 0.0;
+#if FVM_MODE == FVM_MODE_SPMV
+        // the off-diagonal products sit in the row's own CSR positions (the diagonal value
+        // is untouched: it is multiplied in below)
+        const int dpos = b + (int)s_dg[g];
+        int k = b;
+#if FVM_ROW_AHEAD > 0
+        {
+          double v[FVM_ROW_AHEAD];
+#pragma unroll
+          for (int t = 0; t < FVM_ROW_AHEAD; ++t) {
+            v[t] = 0.0;  // (past the row's end / the diagonal: +0.0, exact)
+            if (b + t < e && b + t != dpos) v[t] = s_mat[b + t];
+          }
+#pragma unroll
+          for (int t = 0; t < FVM_ROW_AHEAD; ++t) sC += v[t];
+          k = b + FVM_ROW_AHEAD;
+        }
+#endif
+#pragma unroll 1
+        for (; k < e; ++k)
+          if (k != dpos) sC += s_mat[k];
+#elif FVM_ACC_D || FVM_ACC_C
         int k = b;
 #if FVM_ROW_AHEAD > 0
         {
           // the first shares of the row are loaded together, then added in slot order (a
           // share past the row's end reads as +0.0: exact); the loop below takes the rest
-#if FVM_ACC_D
-          double vD[FVM_ROW_AHEAD];
-#endif
-#if FVM_ACC_C
-          double vC[FVM_ROW_AHEAD];
-#endif
+          double vD[FVM_ROW_AHEAD], vC[FVM_ROW_AHEAD];
 #pragma unroll
           for (int t = 0; t < FVM_ROW_AHEAD; ++t) {
-#if FVM_ACC_D
-            vD[t] = 0.0;
-#endif
-#if FVM_ACC_C
-            vC[t] = 0.0;
-#endif
+            vD[t] = vC[t] = 0.0;
             if (b + t < e - 1) {
 #if FVM_ACC_D
               vD[t] = s_accd[b + t];
@@ -800,12 +819,8 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
           }
 #pragma unroll
           for (int t = 0; t < FVM_ROW_AHEAD; ++t) {
-#if FVM_ACC_D
             sD += vD[t];
-#endif
-#if FVM_ACC_C
             sC += vC[t];
-#endif
           }
           k = b + FVM_ROW_AHEAD;
         }
@@ -819,6 +834,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
           sC += s_accc[k];
 #endif
         }
+#endif
         double x00 = 0.0, x01 = 0.0, x02 = 0.0, u0 = 0.0, cvv = 0.0, sav = 0.0;
 #if FVM_STAGE_X && (FVM_VERT_USES_X)
         {
@@ -840,7 +856,7 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
         sav = s_sa[g];
 #endif
 #if FVM_MODE == FVM_MODE_SPMV
-        sC += s_mat[b + (int)s_dg[g]] * u0;  // the diagonal entry closes the row
+        sC += s_mat[dpos] * u0;  // the diagonal entry closes the row
 #endif
 #if FVM_HAS_VERTEX
         {
@@ -883,6 +899,10 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
       }
     }
     // ---- release the stage to the producer (all lanes of this warp are done)
+#if FVM_MODE == FVM_MODE_SPMV
+    // (the math warps wrote into a stream the next bulk copy -- async proxy -- overwrites)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
     __syncwarp();
     if (lane == 0) fvm_mbar_arrive(empty + st);
   }

@@ -22,6 +22,7 @@ split into contiguous ranges, every rank assembles complete owned rows.
 The reference is single-process; there is no reference code for this file.
 """
 import ctypes
+import os
 from ctypes import byref, c_void_p
 
 import numpy
@@ -204,6 +205,7 @@ class SlabPartition:
         self.n_owned = (j1 - j0) * layer
         self.row_range = (self.n_ghost_lo, self.n_owned)
         self.verts = numpy.arange(g0 * layer, g1 * layer)
+        self.vert_offset = g0 * layer  # local id + offset = global id
         self.recv, self.send = {}, {}
         if j0 > g0:  # ghost layer below: owned by rank - 1; it needs my first layer
             self.recv[rank - 1] = (0, layer)
@@ -305,6 +307,17 @@ class PeerHalo:
         self.n_flags = len(flags)
         self.timeout_ptr = self.buf.ptr + self.flag_off + 8 * part.world
         self.epoch = 0
+        # the whole push as one launch (fvm_halo_push_all): a device table of the peers
+        PEER = numpy.dtype([("idx", "<u8"), ("dst0", "<u8"), ("dst1", "<u8"), ("flag", "<u8"), ("n", "<i8")])
+        tab = numpy.zeros(len(self.peer), dtype=PEER)
+        for i, (p, d) in enumerate(sorted(self.peer.items())):
+            first = d["base"] + d["ghost_byte_off"]
+            tab[i] = (d["send"].ptr, first, first + d["ustride"], d["flag"], d["n"])
+        self.peer_tab = eng.to_device(tab) if len(tab) else None
+        self.push_counters = eng.alloc(4 * max(1, len(tab)))
+        eng._ck(lib.fvm_dev_memset(eng.ctx, self.push_counters.ptr, 0, 4 * max(1, len(tab))))
+        self.max_send = max([d["n"] for d in self.peer.values()], default=0)
+        self.single_launch = int(os.environ.get("FVM_HALO_SINGLE_LAUNCH", "1"))
         if part.world > 1:
             dist.barrier(group=group)  # every mapping exists before the first push
 
@@ -332,9 +345,13 @@ class PeerHalo:
         self.epoch += 1
         k = self.epoch & 1
         src = self.u_ptr(k)
-        for p, d in sorted(self.peer.items()):
-            dst = d["base"] + k * d["ustride"] + d["ghost_byte_off"]
-            eng._ck(lib.fvm_halo_push(eng.ctx, src, d["send"].ptr, d["n"], dst, d["flag"], self.epoch))
+        if self.single_launch and self.peer_tab is not None:
+            eng._ck(lib.fvm_halo_push_all(eng.ctx, self.peer_tab.ptr, len(self.peer), self.max_send,
+                                          src, k, self.epoch, self.push_counters.ptr))
+        else:
+            for p, d in sorted(self.peer.items()):
+                dst = d["base"] + k * d["ustride"] + d["ghost_byte_off"]
+                eng._ck(lib.fvm_halo_push(eng.ctx, src, d["send"].ptr, d["n"], dst, d["flag"], self.epoch))
         if self.n_flags and wait:
             eng._ck(
                 lib.fvm_halo_wait(
@@ -370,10 +387,25 @@ def discretize_linear(obj, part, device=None, fmad=False):
     lp = LinearProblem(obj, part.mesh, device=device, fmad=fmad, row_range=part.row_range)
     A_local, rhs = lp.assemble()
     A = sparse.csr_matrix(
-        (A_local.data, part.verts[A_local.indices].astype(numpy.int32), A_local.indptr),
-        shape=(part.n_owned, part.n_global),
+        (A_local.data, global_columns(part, lp.dmesh), A_local.indptr),
+        shape=(part.n_owned, part.n_global), copy=False,
     )
     return A, rhs
+
+
+def global_columns(part, dmesh):
+    """The pattern's column ids in the GLOBAL numbering (int32), cached with the device
+    mesh.  A slab's local numbering is the global one shifted by its first vertex."""
+    cols = getattr(dmesh, "_global_columns", None)
+    if cols is None:
+        _, indices = dmesh.pattern()
+        off = getattr(part, "vert_offset", None)
+        if off is not None:
+            cols = indices + numpy.int32(off)
+        else:
+            cols = part.verts[indices].astype(numpy.int32)
+        dmesh._global_columns = cols
+    return cols
 
 
 class DistributedFvm:
@@ -446,6 +478,30 @@ class DistributedFvm:
             return None
         return self.halo.fused_wait()
 
+    def step_device(self, mode):
+        """Exchange + launch in one host call (``fvm_halo_step``): pushes the owned boundary
+        values of the NEXT u buffer and evaluates ``mode`` on it.  Falls back to
+        ``exchange()`` + launch when the fused peer halo does not apply."""
+        s, h = self.s, self.halo if self.kind == "peer" else None
+        if (h is None or not self.fused or not h.n_flags or h.peer_tab is None
+                or not s.functors[mode].needs_u or mode == codegen.MODE_LINEAR):
+            u_ptr = self.exchange(mode)
+            (self.residual_device if mode == codegen.MODE_RESIDUAL else self.jacobian_device)(u_ptr)
+            return u_ptr
+        h.epoch += 1
+        k = h.epoch & 1
+        src = h.u_ptr(k)
+        eng = self.eng
+        res = mode == codegen.MODE_RESIDUAL
+        eng._ck(eng.lib.fvm_halo_step(
+            s.dmesh.handle, s.kernels[mode].handle, s._p(s.vmask), s._p(s.dirid), src,
+            None if res else s.data.ptr, self.F.ptr if res else None,
+            h.flag_ptrs.ptr, h.n_flags, h.epoch, h.timeout_ptr,
+            h.peer_tab.ptr, len(h.peer), h.max_send, k, h.push_counters.ptr,
+        ))
+        eng.launches += 1
+        return src
+
     def residual_device(self, u_ptr):
         self.s.launch(codegen.MODE_RESIDUAL, u_ptr=u_ptr, vec_ptr=self.F.ptr,
                       halo=self._halo_arg(codegen.MODE_RESIDUAL))
@@ -458,7 +514,7 @@ class DistributedFvm:
     def eval(self, u_owned):
         """Owned rows of ``f.eval(u)`` [README:121]."""
         self.set_owned(u_owned)
-        self.residual_device(self.exchange(codegen.MODE_RESIDUAL))
+        self.step_device(codegen.MODE_RESIDUAL)
         out = numpy.empty(self.part.n_owned)
         self.F.download(out)
         if self.kind == "peer":
@@ -471,15 +527,15 @@ class DistributedFvm:
         from scipy import sparse
 
         self.set_owned(u_owned)
-        self.jacobian_device(self.exchange(codegen.MODE_JACOBIAN))
+        self.step_device(codegen.MODE_JACOBIAN)
         data = numpy.empty(self.s.nnz)
         self.s.data.download(data)
         if self.kind == "peer":
             self.halo.check_timeout()
-        indptr, indices = self.s.dmesh.pattern()
+        indptr, _ = self.s.dmesh.pattern()
         return sparse.csr_matrix(
-            (data, self.part.verts[indices].astype(numpy.int32), indptr),
-            shape=(self.part.n_owned, self.part.n_global),
+            (data, global_columns(self.part, self.s.dmesh), indptr),
+            shape=(self.part.n_owned, self.part.n_global), copy=False,
         )
 
     def norm2_owned_sq(self):

@@ -41,6 +41,7 @@ class MeshDesc(ctypes.Structure):
         ("control_volumes", c_void_p),
         ("tile_quantum", c_int32),
         ("cell_dim", c_int32),
+        ("coord_cols", c_int32),
     ]
 
 
@@ -112,6 +113,7 @@ SYMBOLS = {
         [c_void_p, c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)],
     ),
     "fvm_kernel_destroy": (c_int, [c_void_p]),
+    "fvm_kernel_cache_stats": (c_int, [POINTER(c_int), POINTER(c_int)]),
     "fvm_kernel_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "fvm_kernel_source": (c_int, [c_char_p, c_char_p, c_size_t, POINTER(c_size_t)]),
     "fvm_assemble": (
@@ -144,6 +146,15 @@ SYMBOLS = {
     "fvm_halo_push": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, ctypes.c_uint64],
+    ),
+    "fvm_halo_push_all": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, ctypes.c_uint64, c_void_p],
+    ),
+    "fvm_halo_step": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+         ctypes.c_uint64, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p],
     ),
     "fvm_halo_wait": (
         c_int,
@@ -321,6 +332,12 @@ class Engine:
             self._kernels[key] = k
         return k
 
+    def kernel_cache_stats(self):
+        """(NVRTC compilations, cubins loaded from the on-disk cache) of this process."""
+        a, b = c_int(), c_int()
+        self.lib.fvm_kernel_cache_stats(byref(a), byref(b))
+        return a.value, b.value
+
     def kernel_source(self, functors):
         need = c_size_t()
         self.lib.fvm_kernel_source(functors.source.encode(), None, 0, byref(need))
@@ -424,7 +441,7 @@ class DeviceMesh:
             if need_el:
                 el = numpy.sqrt(numpy.asarray(mesh.ei_dot_ei, dtype=numpy.float64)).reshape(-1)
                 el = numpy.ascontiguousarray(el)
-            xy = numpy.ascontiguousarray(coords[:, :dim])
+            xy = numpy.ascontiguousarray(coords)  # all columns: the device takes the first dim
             cv = numpy.ascontiguousarray(numpy.asarray(mesh.control_volumes, dtype=numpy.float64))
             assert rec_mask is None or rec_mask.shape == idx0.shape
             self.R = idx0.shape[0]
@@ -433,6 +450,7 @@ class DeviceMesh:
                 index_bytes=idx0.dtype.itemsize, on_device=0, idx0=_ptr(idx0), idx1=_ptr(idx1),
                 ce_ratios=_ptr(ce), edge_len=_ptr(el), rec_mask=_ptr(rec_mask), coords=_ptr(xy),
                 control_volumes=_ptr(cv), tile_quantum=tile_quantum, cell_dim=_cell_dim(mesh),
+                coord_cols=xy.shape[1],
             )
         h = c_void_p()
         eng._ck(eng.lib.fvm_mesh_create(eng.ctx, byref(d), byref(h)))

@@ -264,3 +264,35 @@ def test_odd_length_device_u():
     F_host = f.eval(u)
     F_dev = f.eval(torch.from_numpy(u).cuda())
     assert F_dev.cpu().numpy().tobytes() == F_host.tobytes()
+
+
+def test_cubin_cache_second_process_skips_nvrtc(tmp_path):
+    """The NVRTC output is persisted: a second process with the same functor
+    set loads the cubin from $FVM_CACHE_DIR and never calls nvrtcCompileProgram."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy, pyfvm_b200 as e\n"
+        "from pyfvm_b200 import meshes, engine\n"
+        "from tests import problems\n"
+        "m = meshes.Mesh(*problems.rectangle(17, 11))\n"
+        "A, b = e.discretize_linear(problems.reaction_x(e.form_language), m)\n"
+        "f, j = e.discretize(problems.bratu(e.form_language), m)\n"
+        "f.eval(numpy.zeros(len(m.points))); j.get_linear_operator(numpy.zeros(len(m.points)))\n"
+        "print('STATS', *engine.Engine.get().kernel_cache_stats(), float(abs(A).sum()))\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FVM_CACHE_DIR=str(tmp_path / "cubins"), PYTHONPATH=root)
+    env.pop("FVM_KERNEL_SRC_DIR", None)
+    outs = []
+    for _ in range(2):
+        r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("STATS")][0].split())
+    assert int(outs[0][1]) == 3 and int(outs[0][2]) == 0  # first process: three kernels compiled
+    assert int(outs[1][1]) == 0 and int(outs[1][2]) == 3  # second: none compiled, three loaded
+    assert outs[0][3] == outs[1][3]  # and the same numbers come out
+    assert len(os.listdir(tmp_path / "cubins")) == 3
