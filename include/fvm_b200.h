@@ -187,6 +187,17 @@ int fvm_gen_cube_tetra(fvm_ctx* ctx, int nx, int ny, int nz, int parity, const d
 int fvm_geometry(fvm_ctx* ctx, int cell_dim, int coord_dim, int64_t n_cells, const void* cells_dev,
                  int index_bytes, const double* points_dev, void* idx0_dev, void* idx1_dev,
                  double* ce_dev, double* el_dev);
+/* any simplex mesh: out_dev[v] = 1 (n_vertices bytes, zeroed first) for the vertices of
+ * facets that belong to exactly one cell -- meshplex's is_boundary_point -- from a sort of
+ * the facet keys on the device */
+int fvm_boundary_vertices(fvm_ctx* ctx, int cell_dim, int64_t n_cells, const void* cells_dev,
+                          int index_bytes, int32_t n_vertices, uint8_t* out_dev);
+/* subdomain bits of a cell-restricted dS term for a mesh whose cells live on the device:
+ * rec_mask_dev[r] |= bit for every record r (record order of fvm_geometry) whose cell has
+ * all its vertices flagged in vertex_inside_dev (NULL: every record) */
+int fvm_record_mask(fvm_ctx* ctx, int cell_dim, int64_t n_cells, const void* cells_dev,
+                    int index_bytes, const uint8_t* vertex_inside_dev, uint8_t bit,
+                    uint8_t* rec_mask_dev);
 /* triangle meshes: out_dev[v] = 1 for owned vertices on a boundary edge (an edge that
  * belongs to exactly one cell), from the pattern's half-edge counts */
 int fvm_mesh_boundary_tri(fvm_mesh* mesh, uint8_t* out_dev);

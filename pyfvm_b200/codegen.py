@@ -44,6 +44,8 @@ def tuning(cell_dim=2):
         # ahead of the in-order adds (-1: template defaults)
         "ilp": int(os.environ.get("FVM_ILP", "-1")),
         "setmaxnreg": int(os.environ.get("FVM_SETMAXNREG", "-1")),
+        # math warps (of consumer_warps) that only fold rows; the others only fold slots
+        "row_warps": int(os.environ.get("FVM_ROW_WARPS", "-1")),
         # tiles ahead of the shared-memory fill whose streams are prefetched into L2
         "l2_ahead": int(os.environ.get("FVM_L2_AHEAD", "-1")),
         "row_ahead": int(os.environ.get("FVM_ROW_AHEAD", "-1")),
@@ -226,7 +228,8 @@ def generate(lowered, mode, edge_bits, vert_bits, tune=None):
         raise ValueError(f"undefined functions cannot be lowered to device code: {sorted(bad)}")
 
     for key, macro in (("fold_ahead", "FVM_FOLD_AHEAD"), ("ilp", "FVM_ILP"), ("row_ahead", "FVM_ROW_AHEAD"),
-                       ("setmaxnreg", "FVM_SETMAXNREG"), ("l2_ahead", "FVM_L2_AHEAD")):
+                       ("setmaxnreg", "FVM_SETMAXNREG"), ("l2_ahead", "FVM_L2_AHEAD"),
+                       ("row_warps", "FVM_ROW_WARPS")):
         if tune.get(key, -1) >= 0:
             defs[macro] = tune[key]
     L = [f"// generated by pyfvm_b200.codegen (mode {mode}); do not edit"]

@@ -171,8 +171,8 @@ FVM_HD inline FvmSmemLayout fvm_smem_layout(int max_he, int max_slots, int max_r
   L.dg = o;     o += (mode != FVM_MODE_RESIDUAL) ? fvm_round16(nr * 2u) + 16u : 0u;
   L.mat = o;    o += (mode == FVM_MODE_SPMV) ? fvm_round16((unsigned)max_csr_slots * 8u) + 16u : 0u;
   L.stage_bytes = o;
-  L.bar = 0;  // 2 x 8B mbarriers per stage, then the descriptor-ring mbarriers and slots
-  L.dbar = fvm_round16(16u * (unsigned)stages);
+  L.bar = 0;  // 3 x 8B mbarriers per stage, then the descriptor-ring mbarriers and slots
+  L.dbar = fvm_round16(24u * (unsigned)stages);
   L.ring = fvm_round16(L.dbar + 8u * FVM_NDESC * (unsigned)producers);
   L.stage0 = L.ring + 128u * FVM_NDESC * (unsigned)producers;
   o = L.stage0 + L.stage_bytes * (unsigned)stages;

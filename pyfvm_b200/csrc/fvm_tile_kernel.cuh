@@ -84,6 +84,15 @@
 // tiles give every warp 26 rows; ~17-row tetrahedral tiles keep one warp's lanes busy)
 #define FVM_ROW_RUNS 2
 #endif
+#ifndef FVM_ROW_WARPS
+// 0: every math warp runs the slot pass, a named barrier, then the row pass of the tile.
+// 1: the LAST math warp only runs row passes and the others only slot passes: the slot
+// warps hand a tile's parked shares over through an mbarrier and move on to the next tile
+// (no barrier stall, the row pass of tile i overlaps the slot pass of tile i + 1).
+#define FVM_ROW_WARPS 0
+#endif
+#define FVM_SLOT_WARPS (FVM_CONSUMER_WARPS - FVM_ROW_WARPS)
+#define FVM_NST (32 * FVM_SLOT_WARPS)  // threads of the slot pass
 #ifndef FVM_L2_AHEAD
 #define FVM_L2_AHEAD 0  // experiment (measured: hurts): tiles ahead whose streams are prefetched into L2
 #endif
@@ -500,11 +509,13 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
   const FvmSmemLayout L = a.L;  // computed by the host (fvm_smem_layout)
   unsigned long long* full = (unsigned long long*)(sm + L.bar);
   unsigned long long* empty = full + FVM_STAGES;
+  unsigned long long* parked = empty + FVM_STAGES;  // slot warps -> row warp (FVM_ROW_WARPS)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < FVM_STAGES; ++i) {
       fvm_mbar_init(full + i, FVM_PRODUCERS);        // every producer warp's expect_tx arrival
       fvm_mbar_init(empty + i, FVM_CONSUMER_WARPS);  // one arrival per consumer warp
+      fvm_mbar_init(parked + i, FVM_SLOT_WARPS);     // one arrival per slot warp
     }
     for (int i = 0; i < FVM_PRODUCERS * FVM_NDESC; ++i)
       fvm_mbar_init((unsigned long long*)(sm + L.dbar) + i, 1);
@@ -549,12 +560,19 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
     // pass B row dealing (FVM_ROW_RUNS): blocks of 32 rows (lanes fill first: a 17-row
     // tetrahedral tile keeps one warp busy instead of four warps with 4 lanes each; the warp
     // that takes the first block rotates with the tile) or equal runs of rows per warp
+#if FVM_ROW_WARPS > 0
+    const bool row_role = cw >= FVM_SLOT_WARPS;  // this warp folds rows only
+    const int rw = cw - FVM_SLOT_WARPS;
+    const int g_first = (d_nr * rw) / FVM_ROW_WARPS, g_end = (d_nr * (rw + 1)) / FVM_ROW_WARPS;
+    const int g_step = 32;
+#else
     int g_first = ((cw + it) % FVM_CONSUMER_WARPS) * 32, g_end = d_nr, g_step = FVM_NCT;
     if (FVM_ROW_RUNS == 1 || (FVM_ROW_RUNS == 2 && d_nr >= 64)) {
       g_first = (d_nr * cw) / FVM_CONSUMER_WARPS;
       g_end = (d_nr * (cw + 1)) / FVM_CONSUMER_WARPS;
       g_step = 32;
     }
+#endif
 
 #if FVM_MODE != FVM_MODE_SPMV
     // a tile starts at a slot start: even position of the padded stream, 16-byte aligned
@@ -609,8 +627,11 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
       // scheduler the pass is bound by the latency of one chain, not by issue slots.
       // Lanes past the tile's last slot run on an all-zero metadata word (first pair, row 0,
       // table entry 0: valid addresses, one pair) and store nothing.
+#if FVM_ROW_WARPS > 0
+      if (!row_role)
+#endif
 #pragma unroll 1
-      for (int kb = cw * (32 * FVM_ILP) + lane; kb < d_nk + lane; kb += FVM_NCT * FVM_ILP) {
+      for (int kb = cw * (32 * FVM_ILP) + lane; kb < d_nk + lane; kb += FVM_NST * FVM_ILP) {
         unsigned meta[FVM_ILP];
         int kk[FVM_ILP];
         bool act[FVM_ILP];
@@ -770,9 +791,19 @@ extern "C" __global__ void __launch_bounds__(FVM_THREADS, 4)
           }
         }
       }
+#if FVM_ROW_WARPS > 0
+      if (!row_role) {
+        // hand the tile's parked shares (and the CSR stores) over to the row warp
+        __syncwarp();
+        if (lane == 0) fvm_mbar_arrive(parked + st);
+      } else {
+        fvm_mbar_wait(parked + st, (it / FVM_STAGES) & 1);
+      }
+      if (row_role)
+#else
       // the parked shares (and pass A's CSR stores) are visible to all math warps
       asm volatile("bar.sync 1, %0;" ::"n"(FVM_NCT) : "memory");
-
+#endif
       // ---------------- pass B: one lane per matrix row ------------------------
       for (int g = g_first + lane; g < g_end; g += g_step) {
         const int b = s_rp[g] - d_s0, e = s_rp[g + 1] - d_s0;  // CSR slots of the row

@@ -91,12 +91,56 @@ class DeviceSimplexMesh:
     # -- host side of the attribute contract ---------------------------------------
     @property
     def is_boundary_point(self):
+        """meshplex's ``is_boundary_point``: vertices of facets that belong to exactly one
+        cell, found on the device by a sort of the facet keys (``fvm_boundary_vertices``)
+        unless the flags were supplied (structured grids know them analytically)."""
         if self._boundary is None:
-            raise NotImplementedError(
-                "boundary flags were not supplied; triangle meshes can take them from "
-                "DeviceMesh.boundary_vertices_tri()"
+            eng, n = self.eng, len(self.points)
+            out = eng.alloc(n + 16)
+            eng._ck(
+                eng.lib.fvm_boundary_vertices(
+                    eng.ctx, self.cell_dim, self.n_cells, self._cells.ptr, self.index_bytes, n, out.ptr
+                )
             )
+            flags = numpy.empty(n, dtype=numpy.uint8)
+            out.download(flags)
+            out.free()
+            self._boundary = flags.astype(bool)
         return self._boundary
+
+    def device_record_mask(self, eng, terms):
+        """Per-record subdomain bits of the dS terms, built in HBM (``fvm_record_mask``).
+        ``terms``: list of ``(subdomain or None, bit value)``; a record's cell is inside a
+        subdomain when all its vertices are (meshplex's ``get_cell_mask``).  Returns a
+        device buffer of ``n_records`` bytes carrying a host-side ``digest`` (cache key)."""
+        import hashlib
+
+        assert eng is self.eng
+        R = self.n_records
+        mask = eng.alloc(R + 64)
+        eng._ck(eng.lib.fvm_dev_memset(eng.ctx, mask.ptr, 0, R + 64))
+        h = hashlib.sha256()
+        for subdomain, bit in terms:
+            inside_dev = None
+            if subdomain is not None:
+                if getattr(subdomain, "is_boundary_only", False):
+                    inside = numpy.zeros(len(self.points), dtype=numpy.uint8)  # no cell is "boundary only"
+                else:
+                    inside = numpy.ascontiguousarray(
+                        numpy.asarray(subdomain.is_inside(self.node_coords.T), dtype=bool).astype(numpy.uint8)
+                    )
+                h.update(inside.tobytes())
+                inside_dev = eng.to_device(inside, pad=16)
+            h.update(bytes([bit]))
+            eng._ck(
+                eng.lib.fvm_record_mask(
+                    eng.ctx, self.cell_dim, self.n_cells, self._cells.ptr, self.index_bytes,
+                    None if inside_dev is None else inside_dev.ptr, bit, mask.ptr,
+                )
+            )
+        eng.sync()
+        mask.digest = h.hexdigest()
+        return mask
 
     def get_vertex_mask(self, subdomain=None):
         if subdomain is None:

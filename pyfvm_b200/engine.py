@@ -107,6 +107,10 @@ SYMBOLS = {
         [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "fvm_mesh_boundary_tri": (c_int, [c_void_p, c_void_p]),
+    "fvm_boundary_vertices": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int32, c_void_p]),
+    "fvm_record_mask": (
+        c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p, c_uint8, c_void_p],
+    ),
     "fvm_kernel_create": (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_void_p)]),
     "fvm_kernel_launch_shape": (
         c_int,
@@ -410,7 +414,7 @@ class DeviceMesh:
         self.n = coords.shape[0]
         row_base, n_rows = (0, self.n) if row_range is None else row_range
         self.row_base, self.n_rows = row_base, n_rows
-        if rec_mask is not None:
+        if rec_mask is not None and not isinstance(rec_mask, DeviceBuffer):
             rec_mask = numpy.ascontiguousarray(rec_mask, dtype=numpy.uint8)
         if hasattr(mesh, "device_records"):
             # per-record arrays already live in HBM (pyfvm_b200.device_meshes)
@@ -418,8 +422,10 @@ class DeviceMesh:
             self.R = rec["n_records"]
             keep = [rec]  # keeps the device buffers alive until the mesh is built
             xy = eng.to_device(numpy.ascontiguousarray(coords[:, :dim]))
-            mask_dev = eng.to_device(rec_mask) if rec_mask is not None else None
-            assert rec_mask is None or rec_mask.shape == (self.R,)
+            mask_dev = rec_mask  # built in HBM (DeviceSimplexMesh.device_record_mask) ...
+            if rec_mask is not None and not isinstance(rec_mask, DeviceBuffer):
+                assert rec_mask.shape == (self.R,)
+                mask_dev = eng.to_device(rec_mask)  # ... or handed in as a host array
             d = MeshDesc(
                 dim=dim, n_vertices=self.n, row_base=row_base, n_rows=n_rows, n_records=self.R,
                 index_bytes=rec["index_bytes"], on_device=1, idx0=rec["idx0"], idx1=rec["idx1"],
@@ -610,7 +616,12 @@ def device_mesh(eng, mesh, rec_mask=None, need_el=False, row_range=None, cache=T
     subdomain bits, owned row range) and revalidated against ``mesh_fingerprint`` on
     every hit.  Mesh objects that cannot be weak-referenced are never cached (their
     ``id`` could be reused by another mesh)."""
-    mkey = None if rec_mask is None else hashlib.sha256(rec_mask.tobytes()).hexdigest()
+    if rec_mask is None:
+        mkey = None
+    elif isinstance(rec_mask, DeviceBuffer):
+        mkey = rec_mask.digest
+    else:
+        mkey = hashlib.sha256(rec_mask.tobytes()).hexdigest()
     key = (id(mesh), eng.device, mkey, row_range)
     fp = None
     if cache:

@@ -22,9 +22,19 @@ def _edge_bits(mesh, lowered):
     if all(t.subdomain is None for t in lowered.edge):
         return [None] * len(lowered.edge), None
     if hasattr(mesh, "device_records"):
-        raise NotImplementedError(
-            "dS terms restricted to a subdomain need the cells on the host; use a host mesh"
-        )
+        # cells live in HBM: the per-record bits are built there too
+        terms = []
+        for t in lowered.edge:
+            if t.subdomain is None:
+                bits.append(None)
+                terms.append((None, _KEEP_BIT))
+            else:
+                if nbit >= 7:
+                    raise NotImplementedError("more than 7 subdomain-restricted dS terms")
+                bits.append(nbit)
+                terms.append((t.subdomain, 1 << nbit))
+                nbit += 1
+        return bits, mesh.device_record_mask(Engine.get(), terms)
     idx = numpy.asarray(mesh.idx_hierarchy)
     shape = idx.shape[1:]
     rec_mask = numpy.zeros(shape, dtype=numpy.uint8)

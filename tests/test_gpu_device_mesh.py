@@ -124,3 +124,44 @@ def test_bratu_residual_on_device_slab():
     J = j.get_linear_operator(u)
     parity.assert_pattern_equal(J, J_ref)
     assert (numpy.abs(J.data - J_ref.data) <= 4 * parity.RTOL * s["matrix"].data).all()
+
+
+@pytest.mark.parametrize("kind,args,shuffle", [("rect", (37, 23), False), ("cube", (9,), False),
+                                               ("cube", (8,), True), ("rect", (20, 31), True)])
+def test_boundary_vertices_on_device(kind, args, shuffle):
+    """meshplex's is_boundary_point from a facet sort on the device (2-D and 3-D, any
+    numbering) equals the host provider's."""
+    from pyfvm_b200 import device_meshes as dm
+    from pyfvm_b200 import meshes
+
+    p, c = (problems.rectangle if kind == "rect" else problems.cube)(*args)
+    p, c = meshes.jitter(p, c, scale=0.2, seed=2)
+    if shuffle:
+        p, c = problems.shuffle_numbering(p, c, seed=8)
+    h = meshes.Mesh(p, c)
+    d = dm.DeviceSimplexMesh.from_host(p, c)  # no flags supplied
+    assert numpy.array_equal(d.is_boundary_point, h.is_boundary_point)
+
+
+@pytest.mark.parametrize("kind,args", [("rect", (41, 27)), ("cube", (9,))])
+def test_subdomain_restricted_terms_on_device_mesh(kind, args):
+    """dS terms restricted to a cell subdomain on a mesh whose cells live in HBM: the
+    per-record bits are built on the device (fvm_record_mask)."""
+    import oracle
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import device_meshes as dm
+    from pyfvm_b200 import meshes
+
+    p, c = (problems.rectangle if kind == "rect" else problems.cube)(*args)
+    if kind == "cube":
+        p = p * numpy.array([2.0, 1.0, 1.0])  # LeftHalf is x < 1
+    p, c = meshes.jitter(p, c, scale=0.15, seed=3)
+    h = meshes.Mesh(p, c)
+    d = dm.DeviceSimplexMesh.from_host(p, c)
+    s = {}
+    A_ref, b_ref = oracle.discretize_linear(problems.subdomain_problem(oracle.form_language), h, scales=s)
+    A, b = eng.discretize_linear(problems.subdomain_problem(eng.form_language), d)
+    parity.assert_pattern_equal(A, A_ref)
+    assert (numpy.abs(A.data - A_ref.data) <= 4 * parity.RTOL * s["matrix"].data).all()
+    bound = 4 * parity.RTOL * numpy.maximum(s["rhs"], numpy.abs(b_ref))
+    assert (numpy.abs(b - b_ref) <= bound).all()
