@@ -119,6 +119,9 @@ typedef struct fvm_mesh_desc {
   int32_t tile_quantum; /* 0 = default; half-edges+slots per tile              */
   int32_t cell_dim;     /* 2 triangles, 3 tetrahedra (default tile size; scale of the
                            control volumes derived when control_volumes == NULL)       */
+  int32_t drop_edge_len; /* 1: edge_len only serves to derive the control volumes; its
+                           half-edge stream is freed after the build (functors that read
+                           edge_length then fail at launch) */
   int32_t coord_cols;   /* columns per vertex of the coords array, >= dim (0 = dim): a
                            planar mesh carried with 3 columns needs no sliced host copy */
 } fvm_mesh_desc;
@@ -132,7 +135,9 @@ int fvm_mesh_info(fvm_mesh* mesh, int64_t* nnz, int64_t* n_halfedges, int32_t* n
 /* layout diagnostics, out[0..n): largest tile (half-edges, slots, rows, vertex-table
  * entries), slots whose column lies outside the staged vertex tables (they are
  * gathered from global memory instead), tile quantum, tiles, half-edges, length of the
- * padded half-edge streams (every slot starts even and holds an even number of entries) */
+ * padded half-edge streams (every slot starts even and holds an even number of entries),
+ * row chunks the pattern was built in (> 1: the half-edges did not fit next to their sort
+ * buffers; FVM_BUILD_CHUNK_HE forces a chunk size) */
 int fvm_mesh_stats(fvm_mesh* mesh, int64_t* out, int n);
 /* copy an internal layout array to the host for inspection / tests:
  * 0 = tile descriptors (128 B each), 1 = packed slot metadata (4 B per slot),

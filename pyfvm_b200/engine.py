@@ -41,6 +41,7 @@ class MeshDesc(ctypes.Structure):
         ("control_volumes", c_void_p),
         ("tile_quantum", c_int32),
         ("cell_dim", c_int32),
+        ("drop_edge_len", c_int32),
         ("coord_cols", c_int32),
     ]
 
@@ -432,8 +433,9 @@ class DeviceMesh:
                 ce_ratios=rec["ce"], edge_len=rec["el"],
                 rec_mask=None if mask_dev is None else mask_dev.ptr, coords=xy.ptr,
                 control_volumes=None, tile_quantum=tile_quantum, cell_dim=_cell_dim(mesh),
+                drop_edge_len=0 if need_el else 1,  # kept only when a functor reads edge_length
             )
-            el = True
+            el = True if need_el else None
         else:
             idx = numpy.asarray(mesh.idx_hierarchy)
             idx0 = numpy.ascontiguousarray(idx[0].reshape(-1))
@@ -486,10 +488,10 @@ class DeviceMesh:
 
     def stats(self):
         """Layout diagnostics of the device mesh (see ``fvm_mesh_stats``)."""
-        out = (c_int64 * 9)()
-        self.eng._ck(self.eng.lib.fvm_mesh_stats(self.handle, out, 9))
+        out = (c_int64 * 10)()
+        self.eng._ck(self.eng.lib.fvm_mesh_stats(self.handle, out, 10))
         keys = ["max_he", "max_slots", "max_rows", "max_xtab", "uncovered_slots", "quantum",
-                "tiles", "halfedges", "padded_halfedges"]
+                "tiles", "halfedges", "padded_halfedges", "build_chunks"]
         return dict(zip(keys, [int(x) for x in out]))
 
     def layout(self):

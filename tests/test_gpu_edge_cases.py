@@ -296,3 +296,65 @@ def test_cubin_cache_second_process_skips_nvrtc(tmp_path):
     assert int(outs[1][1]) == 0 and int(outs[1][2]) == 3  # second: none compiled, three loaded
     assert outs[0][3] == outs[1][3]  # and the same numbers come out
     assert len(os.listdir(tmp_path / "cubins")) == 3
+
+
+@pytest.mark.parametrize("kind,args,shuffle", [("rect", (63, 41), False), ("cube", (11,), False),
+                                               ("rect", (37, 29), True), ("cube", (9,), True)])
+def test_chunked_pattern_build_is_bit_identical(kind, args, shuffle, monkeypatch):
+    """The pattern build in row chunks (what lets config 5's 4.8 G half-edges be built on one
+    GPU) must produce byte-identical layouts and results to the one-chunk build."""
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import engine, meshes, problem
+
+    p, c = (problems.rectangle if kind == "rect" else problems.cube)(*args)
+    p, c = meshes.jitter(p, c, scale=0.15, seed=6)
+    if shuffle:
+        p, c = problems.shuffle_numbering(p, c, seed=6)
+    mesh = meshes.Mesh(p, c)
+    P = problems.subdomain_problem(eng.form_language) if kind == "rect" else problems.reaction_x(eng.form_language)
+    out = []
+    for chunk in (None, "4000", "700"):
+        if chunk is None:
+            monkeypatch.delenv("FVM_BUILD_CHUNK_HE", raising=False)
+        else:
+            monkeypatch.setenv("FVM_BUILD_CHUNK_HE", chunk)
+        engine._mesh_cache.clear()
+        lp = problem.LinearProblem(P, mesh)
+        st = lp.dmesh.stats()
+        assert (st["build_chunks"] > 1) == (chunk is not None), st
+        tiles, meta, ce = lp.dmesh.layout()
+        A, b = lp.assemble()
+        out.append((st["build_chunks"], tiles.tobytes(), meta.tobytes(), ce.tobytes(),
+                    A.indptr.tobytes(), A.indices.tobytes(), A.data.tobytes(), b.tobytes(),
+                    lp.dmesh.control_volumes().tobytes()))
+    monkeypatch.delenv("FVM_BUILD_CHUNK_HE", raising=False)
+    engine._mesh_cache.clear()
+    assert out[2][0] > out[1][0] > 1
+    for o in out[1:]:
+        assert o[1:] == out[0][1:]
+
+
+def test_chunked_build_on_device_mesh_derives_control_volumes(monkeypatch):
+    """Device-generated mesh (control volumes derived per chunk from chunk-sized edge-length
+    buffers, edge lengths not kept): same residual bits chunked and unchunked."""
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import device_meshes as dm
+    from pyfvm_b200 import engine
+
+    xs = numpy.linspace(0.0, 1.0, 12)
+    u = 0.2 * numpy.random.default_rng(3).standard_normal(12**3)
+    res = []
+    for chunk in (None, "5000"):
+        if chunk is None:
+            monkeypatch.delenv("FVM_BUILD_CHUNK_HE", raising=False)
+        else:
+            monkeypatch.setenv("FVM_BUILD_CHUNK_HE", chunk)
+        engine._mesh_cache.clear()
+        d = dm.device_cube_tetra(xs, xs, xs)
+        f, j = eng.discretize(problems.bratu(eng.form_language), d)
+        assert not f._s.dmesh.has_el  # Bratu reads no edge_length: the stream is not kept
+        res.append((f._s.dmesh.stats()["build_chunks"], f.eval(u).tobytes(),
+                    j.get_linear_operator(u).data.tobytes(), f._s.dmesh.control_volumes().tobytes()))
+    monkeypatch.delenv("FVM_BUILD_CHUNK_HE", raising=False)
+    engine._mesh_cache.clear()
+    assert res[0][0] == 1 and res[1][0] > 1 and res[0][1:] == res[1][1:]
