@@ -281,6 +281,38 @@ int fvm_bicgstab(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* values_d
                  const double* b_dev, double* x_dev, double* work_dev, double tol, int maxiter,
                  int check_every, int* iters_out, double* relres_out);
 
+/* The same solver on a ROW PARTITION (one process per GPU), still without the host in the
+ * loop: y = A x pushes the owned boundary entries of x into the neighbours' ghost slots
+ * (fvm_halo_push_all) and waits for theirs inside the SpMV kernel, with the epochs held in
+ * device memory so that the captured iteration can be replayed; the three reductions of an
+ * iteration are all-reduces of two doubles over peer memory (every rank stores its partial
+ * sums into every rank's inbox, releases an epoch flag, and adds the world's values in rank
+ * order: identical bits, hence identical control flow, on every rank).  All vectors hold the
+ * owned rows.  The caller maps the peers' buffers (fvm_ipc_*) and fills fvm_dist_args. */
+typedef struct fvm_dist_args {
+  /* halo of x (same layout as fvm_halo_push_all / fvm_spmv_halo) */
+  const void* halo_peers_dev;      /* push table, n_halo_peers records                     */
+  int32_t n_halo_peers;
+  int64_t max_send;
+  uint32_t* push_counters_dev;     /* n_halo_peers zeroed uint32                            */
+  const uint64_t* const* halo_flags_dev; /* flag words my neighbours release               */
+  int32_t n_halo_flags;
+  int32_t* halo_timeout_dev;
+  double* xbuf[2];                 /* my two local x buffers (ghost | owned | ghost)        */
+  int64_t ghost_lo;                /* entries before the owned part                         */
+  uint64_t* halo_epoch_dev;        /* device-resident epoch of this halo (in/out)           */
+  /* all-reduce over peer memory */
+  const void* reduce_peers_dev;    /* world records { double* inbox; uint64_t* flags; }:
+                                      rank r's inbox [2][world][2] and flag words [world]   */
+  int32_t world, rank;
+  uint64_t* reduce_epoch_dev;      /* device-resident epoch of the reductions (in/out)      */
+  int32_t* reduce_timeout_dev;
+} fvm_dist_args;
+int fvm_bicgstab_dist(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* values_dev,
+                      const double* b_dev, double* x_dev, double* work_dev, double tol, int maxiter,
+                      int check_every, const fvm_dist_args* dist, int* iters_out,
+                      double* relres_out);
+
 /* ---- small device helpers used around the path --------------------------------*/
 /* deterministic ||x||_2 (fixed-shape two-stage reduction) [README.md:121 newton] */
 int fvm_norm2(fvm_ctx* ctx, const double* x_dev, int64_t n, double* out);

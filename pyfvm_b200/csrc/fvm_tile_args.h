@@ -103,6 +103,9 @@ struct FvmTileArgs {
   // at tile_rot (interior first), so the NVLink transfer hides behind the interior math
   const unsigned long long* const* halo_flags;  // [n_halo_flags] flag words (or null)
   unsigned long long halo_epoch;
+  // non-null: the epoch to wait for is read from device memory (a launch replayed from a
+  // CUDA graph cannot carry a changing kernel parameter)
+  const unsigned long long* halo_epoch_ptr;
   int* halo_timeout;               // set to 1 when a wait gives up (never hangs)
   int n_halo_flags;
   int ghost_lo_end, ghost_hi_begin;

@@ -189,13 +189,15 @@ __device__ __forceinline__ unsigned fvm_shift_at(long long index, unsigned elem_
 // into its flag word -- the ghost values it pushed over NVLink are then in our HBM --
 // and order the bulk copies (async proxy) after the acquire.  Gives up after ~20 s.
 __device__ __noinline__ void fvm_halo_acquire(const FvmTileArgs& a) {
-  unsigned long long t0;
+  unsigned long long t0, epoch = a.halo_epoch;
+  if (a.halo_epoch_ptr)
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(epoch) : "l"(a.halo_epoch_ptr) : "memory");
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (int i = 0; i < a.n_halo_flags; ++i) {
     for (;;) {
       unsigned long long v;
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.halo_flags[i]) : "memory");
-      if (v >= a.halo_epoch) break;
+      if (v >= epoch) break;
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > 20000000000ull) {

@@ -270,6 +270,7 @@ class PeerHalo:
         self.ustride = (8 * nl + 255) & ~255
         self.flag_off = 2 * self.ustride
         nbytes = self.flag_off + 8 * part.world + 64
+        self.epoch_dev_ptr = None  # set below: [.. | flags | timeout (4) | pad | epoch (8)]
         self.buf = eng.alloc(nbytes)
         eng._ck(lib.fvm_dev_memset(eng.ctx, self.buf.ptr, 0, nbytes))
         eng.sync()
@@ -306,6 +307,7 @@ class PeerHalo:
         self.flag_ptrs = eng.to_device(flags) if len(flags) else None
         self.n_flags = len(flags)
         self.timeout_ptr = self.buf.ptr + self.flag_off + 8 * part.world
+        self.epoch_dev_ptr = self.timeout_ptr + 16  # device copy of the epoch (graph replays)
         self.epoch = 0
         # the whole push as one launch (fvm_halo_push_all): a device table of the peers
         PEER = numpy.dtype([("idx", "<u8"), ("dst0", "<u8"), ("dst1", "<u8"), ("flag", "<u8"), ("n", "<i8")])
@@ -372,6 +374,52 @@ class PeerHalo:
         for d in self.peer.values():
             self.eng.lib.fvm_ipc_close(self.eng.ctx, d["base"])
         self.peer = {}
+
+
+class PeerReduce:
+    """All-reduce of two doubles over peer memory (``k_allreduce2_peer``): every rank owns
+    an inbox ``[2 parities][world][2]`` and a flag word per rank, exported with CUDA IPC;
+    the device table lists every rank's (inbox, flags) as seen from this rank."""
+
+    def __init__(self, part, eng, group=None):
+        import torch.distributed as dist
+
+        self.part, self.eng = part, eng
+        lib, world = eng.lib, part.world
+        self.inbox_bytes = 2 * world * 2 * 8
+        nbytes = self.inbox_bytes + 8 * world + 64
+        self.buf = eng.alloc(nbytes)
+        eng._ck(lib.fvm_dev_memset(eng.ctx, self.buf.ptr, 0, nbytes))
+        eng.sync()
+        self.flags_ptr = self.buf.ptr + self.inbox_bytes
+        self.epoch_ptr = self.flags_ptr + 8 * world
+        self.timeout_ptr = self.epoch_ptr + 16
+        handle = ctypes.create_string_buffer(64)
+        eng._ck(lib.fvm_ipc_export(eng.ctx, self.buf.ptr, handle))
+        handles = [handle.raw]
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, handle.raw, group=group)
+        self._opened = []
+        tab = numpy.zeros((world, 2), dtype=numpy.uint64)
+        for r in range(world):
+            if r == part.rank:
+                base = self.buf.ptr
+            else:
+                b = c_void_p()
+                eng._ck(lib.fvm_ipc_open(eng.ctx, handles[r], byref(b)))
+                base = b.value
+                self._opened.append(base)
+            tab[r] = (base, base + self.inbox_bytes)
+        self.table = eng.to_device(tab)
+        if world > 1:
+            dist.barrier(group=group)
+
+    def close(self):
+        self.eng.sync()
+        for base in self._opened:
+            self.eng.lib.fvm_ipc_close(self.eng.ctx, base)
+        self._opened = []
 
 
 # ---------------------------------------------------------------------------

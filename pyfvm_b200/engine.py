@@ -46,6 +46,27 @@ class MeshDesc(ctypes.Structure):
     ]
 
 
+class DistArgs(ctypes.Structure):
+    # mirrors fvm_dist_args in include/fvm_b200.h
+    _fields_ = [
+        ("halo_peers_dev", c_void_p),
+        ("n_halo_peers", c_int32),
+        ("max_send", c_int64),
+        ("push_counters_dev", c_void_p),
+        ("halo_flags_dev", c_void_p),
+        ("n_halo_flags", c_int32),
+        ("halo_timeout_dev", c_void_p),
+        ("xbuf", c_void_p * 2),
+        ("ghost_lo", c_int64),
+        ("halo_epoch_dev", c_void_p),
+        ("reduce_peers_dev", c_void_p),
+        ("world", c_int32),
+        ("rank", c_int32),
+        ("reduce_epoch_dev", c_void_p),
+        ("reduce_timeout_dev", c_void_p),
+    ]
+
+
 class KernelOpts(ctypes.Structure):
     # mirrors fvm_kernel_opts in include/fvm_b200.h
     _fields_ = [
@@ -142,6 +163,11 @@ SYMBOLS = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int,
          POINTER(c_int), POINTER(c_double)],
+    ),
+    "fvm_bicgstab_dist": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int,
+         c_void_p, POINTER(c_int), POINTER(c_double)],
     ),
     "fvm_norm2": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double)]),
     "fvm_gather_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

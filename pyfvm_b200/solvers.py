@@ -10,7 +10,7 @@ the assembly's own tile kernel in SpMV mode (``fvm_spmv``): same tiles, x gather
 from the staged vertex tables, rows folded in slot order -- deterministic.
 """
 import ctypes
-from ctypes import byref, c_double, c_void_p
+from ctypes import byref, c_double, c_void_p  # noqa: F401
 
 import numpy
 
@@ -221,6 +221,7 @@ class DistributedSystem(DeviceSystem):
         super().__init__(dp.s.dmesh, values_ptr or dp.s.data.ptr, _partitioned=True)
         self.dp, self.part, self.group = dp, dp.part, group
         self.vhalo = PeerHalo(dp.part, self.eng, group=group)  # its own buffers / flags
+        self._reduce = None  # peer-memory all-reduce, mapped on first use
         self._red = torch.zeros(1, dtype=torch.float64, device=f"cuda:{self.eng.device}")
         self._red2 = torch.zeros(2, dtype=torch.float64, device=f"cuda:{self.eng.device}")
 
@@ -251,6 +252,57 @@ class DistributedSystem(DeviceSystem):
         a, b = self._red2.tolist()
         return a, b
 
+    def bicgstab_graph(self, b_ptr, x_ptr, tol=1e-10, maxiter=None, check_every=16):
+        """``A x = b`` from x0 = 0 on the row partition without the host in the loop
+        (``fvm_bicgstab_dist``): the iteration is a CUDA graph, its two halo exchanges push
+        over NVLink with device-resident epochs, its three reductions are peer-memory
+        all-reduces; the host looks at the residual every ``check_every`` iterations."""
+        from .dist import PeerReduce
+        from .engine import DistArgs
+
+        e, n, h = self.eng, self.n, self.vhalo
+        import torch.distributed as dist
+
+        maxiter = maxiter or 20 * int(numpy.sqrt(max(1, self.part.n_global))) + 200
+        if self._reduce is None:
+            self._reduce = PeerReduce(self.part, e, group=self.group)
+        if getattr(self, "_gwork", None) is None:
+            self._gwork = e.alloc(8 * (9 * ((n + 1) & ~1) + 16) + 64)
+        rd = self._reduce
+        if h.epoch & 1:  # start every solve on an even epoch: the graph's buffer order is fixed
+            h.epoch += 1
+        ep = numpy.array([h.epoch], dtype=numpy.uint64)
+        e._ck(e.lib.fvm_h2d(e.ctx, h.epoch_dev_ptr, ep.ctypes.data, 8))
+        args = DistArgs(
+            halo_peers_dev=None if h.peer_tab is None else h.peer_tab.ptr,
+            n_halo_peers=len(h.peer), max_send=h.max_send, push_counters_dev=h.push_counters.ptr,
+            halo_flags_dev=None if h.flag_ptrs is None else h.flag_ptrs.ptr, n_halo_flags=h.n_flags,
+            halo_timeout_dev=h.timeout_ptr, xbuf=(c_void_p * 2)(h.u_ptr(0), h.u_ptr(1)),
+            ghost_lo=self.part.n_ghost_lo, halo_epoch_dev=h.epoch_dev_ptr,
+            reduce_peers_dev=rd.table.ptr, world=self.part.world, rank=self.part.rank,
+            reduce_epoch_dev=rd.epoch_ptr, reduce_timeout_dev=rd.timeout_ptr,
+        )
+        its, rel = ctypes.c_int(), c_double()
+        rc = e.lib.fvm_bicgstab_dist(
+            self.dmesh.handle, e._spmv_kernel, self.values, b_ptr, x_ptr, self._gwork.ptr, tol,
+            maxiter, check_every, ctypes.byref(args), byref(its), byref(rel),
+        )
+        msg = e.lib.fvm_last_error().decode() if rc else ""
+        e._ck(e.lib.fvm_d2h(e.ctx, ep.ctypes.data, h.epoch_dev_ptr, 8))
+        h.epoch = int(ep[0])  # the exchanges the graph replays made
+        if rc != 0:
+            if "BiCGStab" in msg:
+                raise ArithmeticError(f"{msg}: relative residual {rel.value:.3e}")
+            raise RuntimeError(msg)
+        e.launches += 2 * its.value
+        return its.value, rel.value
+
+    def bicgstab(self, b_ptr, x_ptr, tol=1e-10, maxiter=None, x0_is_zero=False, graph=True):
+        if graph and x0_is_zero and int(__import__("os").environ.get("FVM_DIST_GRAPH", "1")):
+            return self.bicgstab_graph(b_ptr, x_ptr, tol=tol, maxiter=maxiter)
+        return super().bicgstab(b_ptr, x_ptr, tol=tol, maxiter=maxiter, x0_is_zero=x0_is_zero,
+                                graph=False)
+
     def matvec(self, x_ptr, y_ptr):
         e, h = self.eng, self.vhalo
         dst = h.u_ptr(h.next_buffer()) + 8 * self.part.n_ghost_lo
@@ -265,6 +317,8 @@ class DistributedSystem(DeviceSystem):
 
     def close(self):
         self.vhalo.close()
+        if self._reduce is not None:
+            self._reduce.close()
 
 
 def newton_distributed(dp, u0_owned, tol=1e-10, max_iter=20, lin_tol=1e-10, verbose=False, group=None):
