@@ -271,8 +271,15 @@ def timed_launches(eng, D, step, steps, warmup, flush_buf=None):
     D.barrier()
     if flush_buf is not None:
         ms = 0.0
+        # (measured: re-aligning the ranks after every flush changes nothing; off by default)
+        align = D.world > 1 and os.environ.get("FVM_BENCH_ALIGN", "0") != "0"
         for _ in range(steps):
             eng._ck(eng.lib.fvm_dev_memset(eng.ctx, flush_buf.ptr, 0, flush_buf.nbytes))
+            if align:
+                # the flush takes a different time on every rank; without re-aligning the ranks a
+                # step that waits for its neighbours' halo would be charged their skew
+                eng.sync()
+                D.barrier()
             eng.timer_begin()
             step()
             ms += eng.timer_end()
