@@ -501,22 +501,30 @@ def run_ours(args):
         return fd.discretize_linear(problem_c4(pe.form_language), part)
 
     e2e_n = max(2, min(args.steps, 4))
-    cold_s = []
-    for i in range(1 + e2e_n):  # (the first call also pays one-off page faults)
+    cold_s, first_s = [], None
+    A_api = b_api = None
+    for i in range(3 + e2e_n):
+        # three untimed calls (W >= 3): the very first one of the process also loads the cubin
+        # (or compiles), pays one-off page faults, and -- from the second request of a size
+        # on -- the engine page-locks its result buffers; its wall time is reported separately
+        A_api = b_api = None  # a caller's loop overwrites its previous result
         pengine._mesh_cache.clear()
         gc.collect()
         eng.sync()
         D.barrier()
         tc = time.time()
         A_api, b_api = api_call()
-        dt = time.time() - tc
-        if i:
-            cold_s.append(D.max([dt])[0])
+        dt = D.max([time.time() - tc])[0]
+        if i == 0:
+            first_s = dt
+        if i >= 3:
+            cold_s.append(dt)
     e2e_s = sum(cold_s) / len(cold_s)
     # the same call again on the SAME mesh object: the device mesh is found in the cache and
     # revalidated against the mesh arrays (identity + sampled content)
     warm_s = []
     for i in range(e2e_n):
+        A_api = b_api = None
         D.barrier()
         tc = time.time()
         A_api, b_api = api_call()
@@ -614,8 +622,10 @@ def run_ours(args):
             # through the plugin objects with host arrays, as scipy's newton_krylov
             # [README:136] and the README's jacobian_solver [README:116] call them
             u_host = numpy.random.default_rng(0).standard_normal(part.n_local)
-            for i in range(1 + e2e_n):
-                if i == 1:
+            # three untimed calls: the engine page-locks a result buffer on the second request
+            # of a size (engine.host_result), which must not land in the timed ones
+            for i in range(3 + e2e_n):
+                if i == 3:
                     tf = time.time()
                 f.eval(u_host)
             res["e2e_host_arrays"] = {
@@ -625,9 +635,11 @@ def run_ours(args):
                 "d2h_bytes_per_step": 8 * n_rows,
                 "what": "f.eval(u) with pageable numpy arrays in and out",
             }
-            for i in range(1 + e2e_n):
-                if i == 1:
+            J = None
+            for i in range(3 + e2e_n):
+                if i == 3:
                     tf = time.time()
+                J = None  # a Newton loop drops the previous operator before asking for the next
                 J = jac.get_linear_operator(u_host)
             jac_leg["e2e_host_arrays"] = {
                 "value": R_global / ((time.time() - tf) / e2e_n),
@@ -689,21 +701,26 @@ def run_ours(args):
             "value": R_global / e2e_s,
             "unit": UNIT,
             "seconds_per_step": e2e_s,
+            "seconds_each_call": [round(t, 4) for t in cold_s],
+            "first_call_of_the_process_s": first_s,
             "h2d_bytes_per_step": int(h2d_cold),
             "d2h_bytes_per_step": int(d2h_cold),
             "what": "pyfvm.discretize_linear(problem, mesh) -- the API call -- on a mesh object the engine "
             "has not seen, pageable numpy in, scipy CSR + numpy rhs out: lowering, upload of the int64 index "
             "hierarchy + geometry, on-device pattern build, assembly, pattern + values + rhs download"
+            "; three untimed calls first (first_call_of_the_process_s: the very first one, incl. cubin "
+            "load and one-off page faults)"
             + ("" if world == 1 else " (every rank calls dist.discretize_linear on its slab; max over ranks)"),
         },
         "e2e_warm": {
             "value": R_global / e2e_warm_s,
             "unit": UNIT,
             "seconds_per_step": e2e_warm_s,
+            "seconds_each_call": [round(t, 4) for t in warm_s],
             "h2d_bytes_per_step": 0,
             "d2h_bytes_per_step": int(8 * nnz + 8 * n_rows),
             "what": "the same API call again on the same mesh object: device mesh cached and revalidated, "
-            "values + rhs downloaded into fresh numpy arrays",
+            "values + rhs downloaded into the engine's page-locked result buffers (numpy views)",
         },
         "e2e_pipelined": pip,
         "roofline": {

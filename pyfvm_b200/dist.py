@@ -563,7 +563,7 @@ class DistributedFvm:
         """Owned rows of ``f.eval(u)`` [README:121]."""
         self.set_owned(u_owned)
         self.step_device(codegen.MODE_RESIDUAL)
-        out = numpy.empty(self.part.n_owned)
+        out = self.eng.host_result(self.part.n_owned, numpy.float64)
         self.F.download(out)
         if self.kind == "peer":
             self.halo.check_timeout()
@@ -576,7 +576,7 @@ class DistributedFvm:
 
         self.set_owned(u_owned)
         self.step_device(codegen.MODE_JACOBIAN)
-        data = numpy.empty(self.s.nnz)
+        data = self.eng.host_result(self.s.nnz, numpy.float64)
         self.s.data.download(data)
         if self.kind == "peer":
             self.halo.check_timeout()

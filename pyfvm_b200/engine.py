@@ -310,16 +310,62 @@ class Engine:
         arr = numpy.ascontiguousarray(arr)
         return self.alloc(arr.nbytes + pad).upload(arr)
 
-    def pinned_empty(self, shape, dtype):
-        """numpy array in page-locked host memory (fast, async-capable copies)."""
-        dtype = numpy.dtype(dtype)
-        n = int(numpy.prod(shape)) if not numpy.isscalar(shape) else int(shape)
-        nbytes = max(1, n * dtype.itemsize)
+    def pinned_raw(self, nbytes):
+        """Page-locked host allocation as a ctypes buffer (freed when it is collected)."""
+        nbytes = max(1, int(nbytes))
         p = c_void_p()
         self._ck(self.lib.fvm_host_alloc(self.ctx, nbytes, byref(p)))
         raw = (ctypes.c_char * nbytes).from_address(p.value)
         weakref.finalize(raw, self.lib.fvm_host_free, self.ctx, c_void_p(p.value))
+        return raw
+
+    def pinned_empty(self, shape, dtype):
+        """numpy array in page-locked host memory (fast, async-capable copies)."""
+        dtype = numpy.dtype(dtype)
+        n = int(numpy.prod(shape)) if not numpy.isscalar(shape) else int(shape)
+        raw = self.pinned_raw(n * dtype.itemsize)
         return numpy.frombuffer(raw, dtype=dtype, count=n).reshape(shape)
+
+    # -- host arrays for results ------------------------------------------------------
+    # A fresh numpy array of 1 GB costs ~45 ms of first-touch page faults on top of the
+    # device -> host copy (measured: 12 GB/s into fresh pageable memory against 50 GB/s
+    # into pinned memory).  Large results are therefore handed out as views of page-locked
+    # buffers from a small pool; a buffer goes back into circulation when the last array
+    # (and scipy matrix) referring to it is gone.  Page-locking itself is slow (~0.25 s per
+    # GB), so a size is only given a pinned buffer from its SECOND request on: a one-shot
+    # discretize_linear never pays for it, a Newton loop pays once.  FVM_PINNED_RESULTS=0
+    # turns the pool off.
+    POOL_MIN_BYTES = 8 << 20
+    POOL_MAX_BYTES = int(os.environ.get("FVM_PINNED_POOL_BYTES", str(6 << 30)))
+
+    def host_result(self, n, dtype):
+        """Uninitialised host array of ``n`` entries for a result download."""
+        import sys
+
+        dtype = numpy.dtype(dtype)
+        nbytes = int(n) * dtype.itemsize
+        if nbytes < self.POOL_MIN_BYTES or os.environ.get("FVM_PINNED_RESULTS", "1") == "0":
+            return numpy.empty(n, dtype=dtype)
+        pool = self.__dict__.setdefault("_result_pool", [])
+        for raw in pool:
+            # referenced only by the pool (+ the loop variable + getrefcount's argument): every
+            # array handed out (and whatever views / scipy matrices hang off it) keeps its
+            # buffer's count up
+            if nbytes <= len(raw) <= nbytes + nbytes // 2 and sys.getrefcount(raw) <= 3:
+                return numpy.frombuffer(raw, dtype=dtype, count=n)
+        seen = self.__dict__.setdefault("_result_sizes", {})
+        seen[nbytes] = seen.get(nbytes, 0) + 1
+        if seen[nbytes] < 2 or sum(len(r) for r in pool) + nbytes > self.POOL_MAX_BYTES:
+            return numpy.empty(n, dtype=dtype)
+        try:
+            raw = self._new_result_buffer((nbytes + (1 << 20) - 1) & ~((1 << 20) - 1))
+        except FvmError:  # no page-locked memory to be had: plain pageable array
+            return numpy.empty(n, dtype=dtype)
+        pool.append(raw)
+        return numpy.frombuffer(raw, dtype=dtype, count=n)
+
+    def _new_result_buffer(self, nbytes):
+        return self.pinned_raw(nbytes)
 
     def sync(self):
         self._ck(self.lib.fvm_ctx_sync(self.ctx))
@@ -551,8 +597,8 @@ class DeviceMesh:
     def pattern(self):
         """Host copy of ``(indptr, indices)`` (int32), fetched once."""
         if self._pattern is None:
-            indptr = numpy.empty(self.n_rows + 1, dtype=numpy.int32)
-            indices = numpy.empty(self.nnz, dtype=numpy.int32)
+            indptr = self.eng.host_result(self.n_rows + 1, numpy.int32)
+            indices = self.eng.host_result(self.nnz, numpy.int32)
             self.eng._ck(
                 self.eng.lib.fvm_mesh_get_pattern(self.handle, _ptr(indptr), _ptr(indices))
             )

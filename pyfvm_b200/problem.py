@@ -216,8 +216,8 @@ class LinearProblem(_DeviceProblem):
             data = self.eng.pinned_empty(self.nnz, numpy.float64)
             rhs = self.eng.pinned_empty(self.n_rows, numpy.float64)
         else:
-            data = numpy.empty(self.nnz)
-            rhs = numpy.empty(self.n_rows)
+            data = self.eng.host_result(self.nnz, numpy.float64)
+            rhs = self.eng.host_result(self.n_rows, numpy.float64)
         self.data.download(data)
         self.vec.download(rhs)
         return self.csr(data), rhs
@@ -277,7 +277,7 @@ class FvmProblem:
             s.eng.sync()
             return out
         self.eval_device(s.upload_u(u))
-        out = numpy.empty(s.n_rows)
+        out = s.eng.host_result(s.n_rows, numpy.float64)
         s.vec.download(out)
         return out
 
@@ -298,7 +298,7 @@ class Jacobian:
         """CSR Jacobian at ``u`` usable by ``spsolve`` [README:116-117]."""
         s = self._s
         self.values_device(s.upload_u(u))
-        data = numpy.empty(s.nnz)
+        data = s.eng.host_result(s.nnz, numpy.float64)
         s.data.download(data)
         return s.csr(data)
 

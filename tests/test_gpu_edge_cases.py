@@ -90,8 +90,10 @@ def test_high_degree_vertex():
     mesh = meshes.Mesh(*_fan(1000))  # centre row: 2000 half-edges, 1001 slots
     _compare_linear(problems.poisson, mesh)
     _compare_linear(problems.reaction_x, mesh)
-    too_big = meshes.Mesh(*_fan(1100))
-    with pytest.raises(engine.FvmError, match="2047"):
+    wider = meshes.Mesh(*_fan(1900))  # 3800 half-edges: the tile quantum shrinks, results hold
+    _compare_linear(problems.reaction_x, wider)
+    too_big = meshes.Mesh(*_fan(2100))
+    with pytest.raises(engine.FvmError, match="4030"):
         _both()[1].discretize_linear(problems.poisson(_both()[1].form_language), too_big)
 
 

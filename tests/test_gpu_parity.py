@@ -139,7 +139,10 @@ def test_readme_bratu_newton():
 
 @pytest.mark.parametrize("name", ["poisson_33x17", "convdiff_33x17", "poisson_cube5"])
 def test_linear_golden(name):
-    """Against the committed fixtures (no oracle at run time)."""
+    """Against the committed fixtures (no oracle at run time).  The fixtures are REGRESSION
+    SNAPSHOTS generated from the repo's own oracle (tests/golden/make_golden.py): they pin
+    the engine to what the oracle produced when they were written, not to the reference
+    (which ships no vectors; parity is unpinned)."""
     import pyfvm_b200 as eng
     from pyfvm_b200 import meshes
 

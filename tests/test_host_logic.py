@@ -171,3 +171,52 @@ def test_mesh_fingerprint_tracks_mutation():
     assert engine.mesh_fingerprint(mesh) != fp0
     other = meshes.Mesh(p, c[::-1].copy())
     assert engine.mesh_fingerprint(other) != fp0
+
+
+def test_result_pool_hands_out_a_buffer_only_when_nobody_holds_it():
+    """engine.host_result (no GPU: the page-locked allocation is replaced by a ctypes
+    buffer): a size gets a pooled buffer from its second request on, a buffer is reused
+    only after every array / scipy matrix over it is gone, small results bypass the pool."""
+    import ctypes
+
+    from pyfvm_b200 import engine
+
+    eng = object.__new__(engine.Engine)
+    made = []
+
+    def fake(nbytes):
+        raw = (ctypes.c_char * nbytes)()
+        made.append(nbytes)
+        return raw
+
+    eng._new_result_buffer = fake
+    n = (engine.Engine.POOL_MIN_BYTES // 8) + 1000
+
+    def addr(a):
+        return a.__array_interface__["data"][0]
+
+    small = eng.host_result(10, numpy.float64)
+    assert small.shape == (10,) and not made
+    first = eng.host_result(n, numpy.float64)  # one-shot callers never pay for page-locking
+    assert not made and first.shape == (n,) and first.dtype == numpy.float64
+    a = eng.host_result(n, numpy.float64)
+    assert len(made) == 1 and made[0] >= 8 * n and made[0] % (1 << 20) == 0
+    b = eng.host_result(n, numpy.float64)  # a is alive: must not alias it
+    assert len(made) == 2 and addr(b) != addr(a)
+    pa = addr(a)
+    a[:] = 1.0
+    # a scipy matrix over the array keeps the buffer busy, and scipy must not copy it
+    # (it does copy slices and reinterpreting views, hence one frombuffer array per result)
+    m = sparse.csr_matrix((a, numpy.arange(n, dtype=numpy.int32), numpy.arange(n + 1, dtype=numpy.int32)),
+                          shape=(n, n), copy=False)
+    assert addr(m.data) == pa
+    del a
+    c = eng.host_result(n, numpy.float64)
+    assert len(made) == 3 and addr(c) not in (pa, addr(b))
+    del m
+    d = eng.host_result(n, numpy.int64)  # free again: reused, any dtype of the same byte size
+    assert len(made) == 3 and addr(d) == pa and d.dtype == numpy.int64
+    # pool cap: beyond it plain arrays
+    eng.POOL_MAX_BYTES = sum(made)
+    e = eng.host_result(n, numpy.float64)
+    assert len(made) == 3 and addr(e) not in (pa, addr(b), addr(c))
