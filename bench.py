@@ -364,22 +364,26 @@ def leg_c5(args, D, N):
         from pyfvm_b200 import solvers
 
         solvers.DeviceSystem(dm, s.data.ptr, _partitioned=True)  # NVRTC-compiles the SpMV kernel
-        D.barrier()
-        ts = time.time()
-        u_own, steps, lin_its = solvers.newton_distributed(
-            dp, numpy.zeros(part.n_owned), tol=args.newton_tol, lin_tol=1e-8, verbose=(D.rank == 0)
-        )
-        D.barrier()
-        umax = D.max([float(u_own.max()) if len(u_own) else 0.0])[0]
-        out["newton_solve"] = {
-            "seconds": time.time() - ts,
-            "newton_steps": steps,
-            "bicgstab_iterations": lin_its,
-            "tol": args.newton_tol,
-            "max_u": umax,
-            "what": "pyfvm.newton from u = 0 with a Jacobi-BiCGStab jacobian_solver, residual / "
-            "Jacobian refresh / SpMV / updates in HBM across the ranks",
-        }
+        out["newton_solve"] = {}
+        for method in args.linear_solver.split(","):
+            D.barrier()
+            ts = time.time()
+            u_own, steps, lin_its = solvers.newton_distributed(
+                dp, numpy.zeros(part.n_owned), tol=args.newton_tol, lin_tol=1e-8, verbose=(D.rank == 0),
+                linear_solver=method,
+            )
+            D.barrier()
+            umax = D.max([float(u_own.max()) if len(u_own) else 0.0])[0]
+            out["newton_solve"][method] = {
+                "seconds": time.time() - ts,
+                "newton_steps": steps,
+                "linear_iterations": lin_its,
+                "spmv_per_iteration": 1 if method == "cg" else 2,
+                "tol": args.newton_tol,
+                "max_u": umax,
+                "what": f"pyfvm.newton from u = 0 with a Jacobi-{method} jacobian_solver, residual / "
+                "Jacobian refresh / SpMV / updates in HBM across the ranks",
+            }
     D.barrier()
     dp.halo.close()
     return out
@@ -921,6 +925,8 @@ def main():
                     help="c4 run: points per side of the config-5-family leg (0: skip)")
     ap.add_argument("--cube", type=int, default=200, help="points per side of the c5 cube")
     ap.add_argument("--solve", action="store_true", help="c5: also run the full Newton solve")
+    ap.add_argument("--linear-solver", default="bicgstab,cg",
+                    help="c5 --solve: comma list of the device Krylov solvers to time (bicgstab, cg)")
     ap.add_argument("--newton-tol", type=float, default=1e-10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

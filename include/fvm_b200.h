@@ -312,6 +312,17 @@ int fvm_bicgstab_dist(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* val
                       const double* b_dev, double* x_dev, double* work_dev, double tol, int maxiter,
                       int check_every, const fvm_dist_args* dist, int* iters_out,
                       double* relres_out);
+/* Jacobi-preconditioned CG for the symmetric case (SURVEY 8f rank 2 names CG next to
+ * BiCGStab; the README's Poisson and Bratu systems [README.md:36-51, 96-121] are symmetric
+ * definite away from their Dirichlet rows): one SpMV and two reductions per iteration,
+ * device-resident scalars, two iterations per replayed CUDA graph.  Starts from the Jacobi
+ * guess x0 = b / diag(A), which solves pyfvm's Dirichlet rows (identity rows whose columns are
+ * NOT eliminated) exactly and so keeps them out of the Krylov space.  dist == NULL: one GPU;
+ * otherwise the row partition of fvm_bicgstab_dist.  work_dev: 4 * ((n + 1) & ~1) + 16
+ * doubles.  Fails with "CG breakdown" when p.Ap and r.(r/d) differ in sign. */
+int fvm_cg(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* values_dev, const double* b_dev,
+           double* x_dev, double* work_dev, double tol, int maxiter, int check_every,
+           const fvm_dist_args* dist_or_null, int* iters_out, double* relres_out);
 
 /* ---- small device helpers used around the path --------------------------------*/
 /* deterministic ||x||_2 (fixed-shape two-stage reduction) [README.md:121 newton] */

@@ -169,6 +169,11 @@ SYMBOLS = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int,
          c_void_p, POINTER(c_int), POINTER(c_double)],
     ),
+    "fvm_cg": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int,
+         c_void_p, POINTER(c_int), POINTER(c_double)],
+    ),
     "fvm_norm2": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_double)]),
     "fvm_gather_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "fvm_ipc_export": (c_int, [c_void_p, c_void_p, c_char_p]),

@@ -85,6 +85,50 @@ class DeviceSystem:
         e.launches += 2 * its.value
         return its.value, rel.value
 
+    def _dist_args(self):
+        return None  # one GPU: no halo, no all-reduce
+
+    def _after_graph_solve(self):
+        pass
+
+    def cg(self, b_ptr, x_ptr, tol=1e-10, maxiter=None, check_every=16):
+        """``A x = b`` for a symmetric definite ``A`` (Dirichlet rows as pyfvm writes them
+        are fine) with ``fvm_cg``: Jacobi-preconditioned CG from x0 = b / diag(A), one SpMV
+        and two reductions per iteration, scalars in HBM, CUDA graph replayed between host
+        looks at the residual.  On a row partition the halo pushes and the all-reduces go
+        over peer memory.  Returns (iterations, relative residual); ``ArithmeticError`` on
+        breakdown (an indefinite or unsymmetric matrix) or no convergence."""
+        e, n = self.eng, self.n
+        maxiter = maxiter or self._default_maxiter()
+        if getattr(self, "_gwork", None) is None:
+            self._gwork = e.alloc(8 * (9 * ((n + 1) & ~1) + 16) + 64)
+        args = self._dist_args()
+        its, rel = ctypes.c_int(), c_double()
+        rc = e.lib.fvm_cg(
+            self.dmesh.handle, e._spmv_kernel, self.values, b_ptr, x_ptr, self._gwork.ptr, tol,
+            maxiter, check_every, None if args is None else ctypes.byref(args), byref(its), byref(rel),
+        )
+        msg = e.lib.fvm_last_error().decode() if rc else ""
+        self._after_graph_solve()
+        if rc != 0:
+            if msg.startswith("CG "):
+                raise ArithmeticError(f"{msg}: relative residual {rel.value:.3e}")
+            raise RuntimeError(msg)
+        e.launches += its.value + 1
+        return its.value, rel.value
+
+    def _default_maxiter(self):
+        return 20 * int(numpy.sqrt(self.n)) + 200
+
+    def solve(self, b_ptr, x_ptr, method="bicgstab", tol=1e-10, maxiter=None):
+        """``A x = b`` from the solver's own initial guess; ``method``: "bicgstab" (any
+        matrix) or "cg" (symmetric definite)."""
+        if method == "cg":
+            return self.cg(b_ptr, x_ptr, tol=tol, maxiter=maxiter)
+        if method != "bicgstab":
+            raise ValueError(f"unknown linear solver {method!r} (bicgstab, cg)")
+        return self.bicgstab(b_ptr, x_ptr, tol=tol, maxiter=maxiter, x0_is_zero=True)
+
     def bicgstab(self, b_ptr, x_ptr, tol=1e-10, maxiter=None, x0_is_zero=False, graph=True):
         """Solve ``A x = b`` (device pointers), right-preconditioned with the
         diagonal.  Stops at ``||r|| <= tol * ||b||``.  Returns (iterations,
@@ -147,19 +191,20 @@ class DeviceSystem:
         raise ArithmeticError(f"BiCGStab did not converge: relative residual {res / bnorm:.3e}")
 
 
-def solve_linear(lp, tol=1e-10, maxiter=None):
-    """``discretize_linear`` + solve, all on the device: assemble, BiCGStab, and only
-    the solution comes back (host array)."""
+def solve_linear(lp, tol=1e-10, maxiter=None, method="bicgstab"):
+    """``discretize_linear`` + solve, all on the device: assemble, BiCGStab (or CG for a
+    symmetric definite system, ``method="cg"``), and only the solution comes back (host
+    array)."""
     lp.assemble_device()
     sysm = DeviceSystem(lp.dmesh, lp.data.ptr)
     x = lp.eng.alloc(8 * lp.n)
-    iters, relres = sysm.bicgstab(lp.vec.ptr, x.ptr, tol=tol, maxiter=maxiter, x0_is_zero=True)
+    iters, relres = sysm.solve(lp.vec.ptr, x.ptr, method=method, tol=tol, maxiter=maxiter)
     out = numpy.empty(lp.n)
     x.download(out)
     return out, iters, relres
 
 
-def jacobian_solver(jacobian, tol=1e-10, maxiter=None):
+def jacobian_solver(jacobian, tol=1e-10, maxiter=None, method="bicgstab"):
     """A ``jacobian_solver(u0, rhs) -> du`` callback for ``pyfvm.newton`` [README:113-117]
     that refreshes the Jacobian values and solves on the device."""
     s = jacobian._s
@@ -169,7 +214,7 @@ def jacobian_solver(jacobian, tol=1e-10, maxiter=None):
     def solver(u0, rhs):
         jacobian.values_device(s.upload_u(u0))
         b.upload(numpy.ascontiguousarray(rhs, dtype=numpy.float64))
-        sysm.bicgstab(b.ptr, x.ptr, tol=tol, maxiter=maxiter, x0_is_zero=True)
+        sysm.solve(b.ptr, x.ptr, method=method, tol=tol, maxiter=maxiter)
         du = numpy.empty(s.n)
         x.download(du)
         return du
@@ -177,10 +222,12 @@ def jacobian_solver(jacobian, tol=1e-10, maxiter=None):
     return solver
 
 
-def newton_device(f, jacobian, u0, tol=1e-10, max_iter=20, lin_tol=1e-10, verbose=False):
+def newton_device(f, jacobian, u0, tol=1e-10, max_iter=20, lin_tol=1e-10, verbose=False,
+                  linear_solver="bicgstab"):
     """``pyfvm.newton`` [README:121] with everything in HBM: residual, norm,
-    Jacobian refresh, BiCGStab and the update; one double per step crosses PCIe.
-    Same stopping rule and iteration cap as the reference's newton."""
+    Jacobian refresh, BiCGStab (``linear_solver="cg"``: CG, for symmetric definite
+    Jacobians such as Bratu's [README:96-110]) and the update; one double per step crosses
+    PCIe.  Same stopping rule and iteration cap as the reference's newton."""
     s = f._s
     e, n = s.eng, s.n
     sysm = DeviceSystem(s.dmesh, s.data.ptr)
@@ -198,7 +245,7 @@ def newton_device(f, jacobian, u0, tol=1e-10, max_iter=20, lin_tol=1e-10, verbos
             raise RuntimeError(f"Newton did not converge in {max_iter} steps (||F|| = {nrm:e})")
         jacobian.values_device(u_ptr)
         # J du = -F: solve for +F and subtract
-        sysm.bicgstab(s.vec.ptr, du.ptr, tol=lin_tol, x0_is_zero=True)
+        sysm.solve(s.vec.ptr, du.ptr, method=linear_solver, tol=lin_tol)
         e._ck(e.lib.fvm_axpy(e.ctx, -1.0, du.ptr, u_ptr, n))
         steps += 1
     out = numpy.empty(n)
@@ -252,28 +299,24 @@ class DistributedSystem(DeviceSystem):
         a, b = self._red2.tolist()
         return a, b
 
-    def bicgstab_graph(self, b_ptr, x_ptr, tol=1e-10, maxiter=None, check_every=16):
-        """``A x = b`` from x0 = 0 on the row partition without the host in the loop
-        (``fvm_bicgstab_dist``): the iteration is a CUDA graph, its two halo exchanges push
-        over NVLink with device-resident epochs, its three reductions are peer-memory
-        all-reduces; the host looks at the residual every ``check_every`` iterations."""
+    def _default_maxiter(self):
+        return 20 * int(numpy.sqrt(max(1, self.part.n_global))) + 200
+
+    def _dist_args(self):
+        """The halo and all-reduce tables of this rank for the graph-replayed solvers; the
+        device-resident halo epoch is brought in step with the host's first."""
         from .dist import PeerReduce
         from .engine import DistArgs
 
-        e, n, h = self.eng, self.n, self.vhalo
-        import torch.distributed as dist
-
-        maxiter = maxiter or 20 * int(numpy.sqrt(max(1, self.part.n_global))) + 200
+        e, h = self.eng, self.vhalo
         if self._reduce is None:
             self._reduce = PeerReduce(self.part, e, group=self.group)
-        if getattr(self, "_gwork", None) is None:
-            self._gwork = e.alloc(8 * (9 * ((n + 1) & ~1) + 16) + 64)
         rd = self._reduce
         if h.epoch & 1:  # start every solve on an even epoch: the graph's buffer order is fixed
             h.epoch += 1
         ep = numpy.array([h.epoch], dtype=numpy.uint64)
         e._ck(e.lib.fvm_h2d(e.ctx, h.epoch_dev_ptr, ep.ctypes.data, 8))
-        args = DistArgs(
+        return DistArgs(
             halo_peers_dev=None if h.peer_tab is None else h.peer_tab.ptr,
             n_halo_peers=len(h.peer), max_send=h.max_send, push_counters_dev=h.push_counters.ptr,
             halo_flags_dev=None if h.flag_ptrs is None else h.flag_ptrs.ptr, n_halo_flags=h.n_flags,
@@ -282,14 +325,30 @@ class DistributedSystem(DeviceSystem):
             reduce_peers_dev=rd.table.ptr, world=self.part.world, rank=self.part.rank,
             reduce_epoch_dev=rd.epoch_ptr, reduce_timeout_dev=rd.timeout_ptr,
         )
+
+    def _after_graph_solve(self):
+        e, h = self.eng, self.vhalo
+        ep = numpy.zeros(1, dtype=numpy.uint64)
+        e._ck(e.lib.fvm_d2h(e.ctx, ep.ctypes.data, h.epoch_dev_ptr, 8))
+        h.epoch = int(ep[0])  # the exchanges the graph replays made
+
+    def bicgstab_graph(self, b_ptr, x_ptr, tol=1e-10, maxiter=None, check_every=16):
+        """``A x = b`` from x0 = 0 on the row partition without the host in the loop
+        (``fvm_bicgstab_dist``): the iteration is a CUDA graph, its two halo exchanges push
+        over NVLink with device-resident epochs, its three reductions are peer-memory
+        all-reduces; the host looks at the residual every ``check_every`` iterations."""
+        e, n = self.eng, self.n
+        maxiter = maxiter or self._default_maxiter()
+        if getattr(self, "_gwork", None) is None:
+            self._gwork = e.alloc(8 * (9 * ((n + 1) & ~1) + 16) + 64)
+        args = self._dist_args()
         its, rel = ctypes.c_int(), c_double()
         rc = e.lib.fvm_bicgstab_dist(
             self.dmesh.handle, e._spmv_kernel, self.values, b_ptr, x_ptr, self._gwork.ptr, tol,
             maxiter, check_every, ctypes.byref(args), byref(its), byref(rel),
         )
         msg = e.lib.fvm_last_error().decode() if rc else ""
-        e._ck(e.lib.fvm_d2h(e.ctx, ep.ctypes.data, h.epoch_dev_ptr, 8))
-        h.epoch = int(ep[0])  # the exchanges the graph replays made
+        self._after_graph_solve()
         if rc != 0:
             if "BiCGStab" in msg:
                 raise ArithmeticError(f"{msg}: relative residual {rel.value:.3e}")
@@ -321,7 +380,8 @@ class DistributedSystem(DeviceSystem):
             self._reduce.close()
 
 
-def newton_distributed(dp, u0_owned, tol=1e-10, max_iter=20, lin_tol=1e-10, verbose=False, group=None):
+def newton_distributed(dp, u0_owned, tol=1e-10, max_iter=20, lin_tol=1e-10, verbose=False, group=None,
+                       linear_solver="bicgstab"):
     """``pyfvm.newton`` [README:121] on a row partition (one rank per GPU): residual,
     Jacobian refresh, BiCGStab and update stay in HBM; per step a handful of
     doubles cross NCCL (norms / dot products) and the ghost values cross NVLink.
@@ -346,7 +406,7 @@ def newton_distributed(dp, u0_owned, tol=1e-10, max_iter=20, lin_tol=1e-10, verb
             if steps >= max_iter:
                 raise RuntimeError(f"Newton did not converge in {max_iter} steps (||F|| = {nrm:e})")
             dp.jacobian_device(u_ptr)
-            its, _ = sysm.bicgstab(dp.F.ptr, du.ptr, tol=lin_tol, x0_is_zero=True)
+            its, _ = sysm.solve(dp.F.ptr, du.ptr, method=linear_solver, tol=lin_tol)
             lin_its += its
             dp.halo.check_timeout()  # a halo wait that gave up must not feed the next step
             sysm.vhalo.check_timeout()

@@ -185,8 +185,34 @@ def gpu_worker():
             print(f"distributed BiCGStab: graph its={xs[0][0]} relres={xs[0][1]:.2e}; host-driven "
                   f"its={xs[1][0]} relres={xs[1][1]:.2e}; max diff {dk:.2e}: ok={good}", flush=True)
         ok &= good
+        # row-partitioned CG (fvm_cg with the halo / all-reduce tables) on the same symmetric
+        # Jacobian system: same solution as BiCGStab, and the same bits on a second run
+        xc = []
+        for _ in range(2):
+            xd = dp.eng.alloc(8 * max(1, part.n_owned) + 16)
+            its_c, rel_c = sysm.cg(dp.F.ptr, xd.ptr, tol=1e-10)
+            x = numpy.empty(part.n_owned)
+            xd.download(x)
+            xc.append(x)
+        dc = float(numpy.abs(xc[0] - xs[1][2]).max()) if part.n_owned else 0.0
+        good = rel_c <= 1e-10 and dc <= 1e-7 * max(scale, 1e-30) and xc[0].tobytes() == xc[1].tobytes()
+        if rank == 0:
+            print(f"distributed CG: its={its_c} relres={rel_c:.2e}; max diff to BiCGStab {dc:.2e}; "
+                  f"repeatable bits: ok={good}", flush=True)
+        ok &= good
         dist.barrier()
         sysm.close()
+        dp.halo.close()
+        # distributed Newton again with CG as the linear solver
+        dp = fd.DistributedFvm(prob, part, halo="peer")
+        u_cg, steps_cg, its_cg = solvers.newton_distributed(dp, numpy.zeros(part.n_owned), linear_solver="cg")
+        dcg = float(numpy.abs(u_cg - u_own).max()) if part.n_owned else 0.0
+        good = steps_cg == steps and dcg <= 1e-8
+        if rank == 0:
+            print(f"distributed Newton with CG: steps={steps_cg}, CG its={its_cg}, "
+                  f"max |u - u_bicgstab| = {dcg:.2e}: ok={good}", flush=True)
+        ok &= good
+        dist.barrier()
         dp.halo.close()
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # any rank's failure fails the run

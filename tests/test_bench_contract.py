@@ -66,4 +66,5 @@ def test_config5_full_size_table():
     assert all("343^3" in d["config"]["workload"] for d in t)
     for a, b in zip(t, t[1:]):
         assert b["n_gpus"] == 2 * a["n_gpus"] and b["ms_per_step"] < 0.6 * a["ms_per_step"]
-    assert t[3]["newton_solve"]["newton_steps"] == 2
+    ns = t[3]["newton_solve"]
+    assert ns.get("bicgstab", ns)["newton_steps"] == 2  # (one record per Krylov solver since CG exists)
