@@ -71,6 +71,15 @@ int fvm_ctx_info(fvm_ctx* ctx, char* name, size_t name_len, int* sm_count, size_
 /* ---- device / pinned memory (so a host binding needs no other GPU library) */
 int fvm_dev_alloc(fvm_ctx* ctx, size_t bytes, void** out_dev);
 int fvm_dev_free(fvm_ctx* ctx, void* ptr_dev);
+/* Device memory released through this library (fvm_dev_free, fvm_mesh_destroy, build
+ * temporaries) is kept in a per-device block cache and handed out again to requests of
+ * nearly the same size (FVM_DEVICE_CACHE_BYTES, default 24 GB; 0 turns it off): the repeated
+ * discretize_linear(problem, mesh) calls of [README.md:49] otherwise pay cudaMalloc/cudaFree
+ * of several GB each time.  Blocks exported with fvm_ipc_export are never recycled. */
+int fvm_device_cache_stats(fvm_ctx* ctx, int64_t* idle_bytes, int64_t* idle_blocks,
+                           int64_t* live_blocks);
+/* give every idle block back to the driver (e.g. before another library needs the memory) */
+int fvm_device_cache_flush(fvm_ctx* ctx);
 int fvm_dev_memset(fvm_ctx* ctx, void* ptr_dev, int value, size_t bytes);
 int fvm_h2d(fvm_ctx* ctx, void* dst_dev, const void* src, size_t bytes);
 int fvm_d2h(fvm_ctx* ctx, void* dst, const void* src_dev, size_t bytes);

@@ -169,6 +169,8 @@ SYMBOLS = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int,
          c_void_p, POINTER(c_int), POINTER(c_double)],
     ),
+    "fvm_device_cache_stats": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    "fvm_device_cache_flush": (c_int, [c_void_p]),
     "fvm_cg": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int,
@@ -371,6 +373,16 @@ class Engine:
 
     def _new_result_buffer(self, nbytes):
         return self.pinned_raw(nbytes)
+
+    def device_cache_stats(self):
+        """(idle bytes, idle blocks, live blocks) of this device's block cache."""
+        a, b, c = c_int64(), c_int64(), c_int64()
+        self._ck(self.lib.fvm_device_cache_stats(self.ctx, byref(a), byref(b), byref(c)))
+        return a.value, b.value, c.value
+
+    def device_cache_flush(self):
+        """Give the cached idle device blocks back to the driver."""
+        self._ck(self.lib.fvm_device_cache_flush(self.ctx))
 
     def sync(self):
         self._ck(self.lib.fvm_ctx_sync(self.ctx))

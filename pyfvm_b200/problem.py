@@ -7,6 +7,8 @@ Reference surface reproduced here:
 * ``f.eval(u) -> ndarray``                                           [README:121, 136]
 * ``jacobian.get_linear_operator(u0) -> scipy CSR``                  [README:116]
 """
+import concurrent.futures
+
 import numpy
 from scipy import sparse
 
@@ -52,6 +54,21 @@ def _edge_bits(mesh, lowered):
     return bits, numpy.ascontiguousarray(rec_mask.reshape(-1))
 
 
+def _vertex_term_bits(lowered):
+    """Bit number of every vertex term's subdomain (None: everywhere) -- what the code
+    generator needs; the masks themselves (`_vertex_bits`) are only needed at launch."""
+    bits, nbit = [], 0
+    for t in lowered.vertex:
+        if t.subdomain is None:
+            bits.append(None)
+            continue
+        if nbit >= 8:
+            raise NotImplementedError("more than 8 subdomain-restricted dV terms")
+        bits.append(nbit)
+        nbit += 1
+    return bits
+
+
 def _vertex_bits(mesh, lowered, n):
     bits, vmask, nbit = [], None, 0
     for t in lowered.vertex:
@@ -92,8 +109,7 @@ class _DeviceProblem:
         lower = lowering.lower_linear if kind == "linear" else lowering.lower_nonlinear
         self.lowered = lowered = lower(obj, dim)
         ebits, rec_mask = _edge_bits(mesh, lowered)
-        vbits, vmask = _vertex_bits(mesh, lowered, n)
-        dirid = _dirichlet_ids(mesh, lowered, n)
+        vbits = _vertex_term_bits(lowered)
         modes = (
             [codegen.MODE_LINEAR]
             if kind == "linear"
@@ -102,10 +118,28 @@ class _DeviceProblem:
         tune = codegen.tuning(_cell_dim(mesh))
         self.functors = {m: codegen.generate(lowered, m, ebits, vbits, tune) for m in modes}
         need_el = any(f.uses_el for f in self.functors.values())
-        # row_range = (first owned vertex, owned rows): row-partitioned multi-GPU runs
-        self.dmesh = device_mesh(
-            eng, mesh, rec_mask=rec_mask, need_el=need_el, row_range=row_range
-        )
+        # row_range = (first owned vertex, owned rows): row-partitioned multi-GPU runs.
+        # The device mesh (upload + pattern build: one long GIL-free library call) is made on
+        # a helper thread while this one evaluates the user's subdomain predicates on the
+        # vertices (numpy, ~15 ms per 16 M vertices); their uploads wait for the join --
+        # they share the engine's bounce buffers with the mesh upload.
+        # (Device-resident meshes answer those predicates with library calls of their own on
+        # the same context: no overlap for them.)
+        if hasattr(mesh, "device_records"):
+            self.dmesh = device_mesh(eng, mesh, rec_mask=rec_mask, need_el=need_el, row_range=row_range)
+            _, vmask = _vertex_bits(mesh, lowered, n)
+            dirid = _dirichlet_ids(mesh, lowered, n)
+        else:
+            with concurrent.futures.ThreadPoolExecutor(1) as pool:
+                fut = pool.submit(
+                    device_mesh, eng, mesh, rec_mask=rec_mask, need_el=need_el, row_range=row_range
+                )
+                try:
+                    _, vmask = _vertex_bits(mesh, lowered, n)
+                    dirid = _dirichlet_ids(mesh, lowered, n)
+                finally:
+                    concurrent.futures.wait([fut])
+                self.dmesh = fut.result()
         if any(f.uses_sa for f in self.functors.values()) and not self.dmesh.has_sa:
             if not hasattr(mesh, "surface_areas"):
                 raise NotImplementedError(

@@ -360,3 +360,50 @@ def test_chunked_build_on_device_mesh_derives_control_volumes(monkeypatch):
     monkeypatch.delenv("FVM_BUILD_CHUNK_HE", raising=False)
     engine._mesh_cache.clear()
     assert res[0][0] == 1 and res[1][0] > 1 and res[0][1:] == res[1][1:]
+
+
+def test_device_block_cache_recycles_poisoned_blocks(monkeypatch):
+    """The block cache: a dropped mesh's arrays and the build temporaries are
+    handed out again.  With FVM_CACHE_POISON=1 every recycled block comes back full of NaN bit
+    patterns, so the rebuilt mesh + assembly must not depend on fresh memory being zero:
+    same bits as the first build, and the oracle's values."""
+    import gc
+
+    import oracle
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import engine, meshes
+
+    e = engine.Engine.get()
+    monkeypatch.setenv("FVM_CACHE_POISON", "1")
+    p, c = problems.rectangle(143, 97)
+    p, c = meshes.jitter(p, c, scale=0.2, seed=4)
+    mesh = meshes.Mesh(p, c)
+    prob = problems.convection_diffusion
+
+    def run():
+        engine._mesh_cache.clear()  # a fresh device mesh (and pattern build) every time
+        gc.collect()
+        A, b = eng.discretize_linear(prob(eng.form_language), mesh)
+        return A.indptr.copy(), A.indices.copy(), A.data.copy(), b.copy()
+
+    first = run()
+    gc.collect()
+    idle_bytes, idle_blocks, _ = e.device_cache_stats()
+    assert idle_blocks > 0 and idle_bytes > 0  # the first build's blocks are waiting
+    second = run()
+    gc.collect()
+    for a, b in zip(first, second):
+        assert a.tobytes() == b.tobytes()
+    A_ref, b_ref = oracle.discretize_linear(prob(oracle.form_language), mesh)
+    assert numpy.array_equal(first[0], A_ref.indptr) and numpy.array_equal(first[1], A_ref.indices)
+    assert numpy.abs(second[2] - A_ref.data).max() <= 1e-13 * numpy.abs(A_ref.data).max()
+    assert numpy.abs(second[3] - b_ref).max() <= 1e-13 * max(1.0, numpy.abs(b_ref).max())
+    # residual / Jacobian / SpMV on recycled blocks too
+    f, jac = eng.discretize(problems.bratu(eng.form_language), mesh)
+    u = 0.1 * numpy.random.default_rng(0).standard_normal(len(p))
+    fo, jo = oracle.discretize(problems.bratu(oracle.form_language), mesh)
+    assert numpy.abs(f.eval(u) - fo.eval(u)).max() <= 1e-12
+    J, Jo = jac.get_linear_operator(u), jo.get_linear_operator(u)
+    assert numpy.abs(J.data - Jo.data).max() <= 1e-13 * numpy.abs(Jo.data).max()
+    e.device_cache_flush()
+    assert e.device_cache_stats()[0] == 0
