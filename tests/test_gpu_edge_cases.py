@@ -407,3 +407,51 @@ def test_device_block_cache_recycles_poisoned_blocks(monkeypatch):
     assert numpy.abs(J.data - Jo.data).max() <= 1e-13 * numpy.abs(Jo.data).max()
     e.device_cache_flush()
     assert e.device_cache_stats()[0] == 0
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_bank_steering_changes_no_bits(shuffle, monkeypatch):
+    """A triangle mesh's vertex tables are re-laid (bank steering) on the mesh's
+    second launch: the first (unsteered) and later (steered) launches, and a mesh that is
+    never steered (FVM_BANK_STEERING=0), must produce the same bits in every mode."""
+    import gc
+
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import engine, meshes, solvers
+
+    p, c = problems.rectangle(211, 157)
+    p, c = meshes.jitter(p, c, scale=0.2, seed=2)
+    if shuffle:
+        p, c = problems.shuffle_numbering(p, c, seed=3)
+    mesh = meshes.Mesh(p, c)
+    u = 0.1 * numpy.random.default_rng(1).standard_normal(len(p))
+
+    def run():
+        engine._mesh_cache.clear()
+        gc.collect()
+        out = []
+        lp = eng.problem.LinearProblem(problems.convection_diffusion(eng.form_language), mesh)
+        for _ in range(3):  # launch 1: natural tables; launches 2, 3: steered (if enabled)
+            A, b = lp.assemble()
+            out.append((A.data.copy(), b.copy()))
+        xtab = lp.dmesh.stats()["max_xtab"]
+        f, jac = eng.discretize(problems.bratu(eng.form_language), mesh)
+        F = f.eval(u).copy()
+        J = jac.get_linear_operator(u).data.copy()
+        sysm = solvers.DeviceSystem(lp.dmesh, lp.data.ptr)
+        xd, yd = lp.eng.to_device(u, pad=16), lp.eng.alloc(8 * lp.n + 16)
+        sysm.matvec(xd.ptr, yd.ptr)
+        y = numpy.empty(lp.n)
+        yd.download(y)
+        return out, F, J, y, xtab
+
+    monkeypatch.setenv("FVM_BANK_STEERING", "1")
+    on = run()
+    monkeypatch.setenv("FVM_BANK_STEERING", "0")
+    off = run()
+    for (d0, b0) in on[0] + off[0]:
+        assert d0.tobytes() == on[0][0][0].tobytes() and b0.tobytes() == on[0][0][1].tobytes()
+    for a, b in zip(on[1:4], off[1:4]):
+        assert a.tobytes() == b.tobytes()
+    if not shuffle:
+        assert on[4] >= off[4]  # the steered tables stage a few extra vertices

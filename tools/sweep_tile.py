@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--fmad", type=int, default=0)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--steering", default="1", help="FVM_BANK_STEERING values to build meshes with")
     args = ap.parse_args()
     ints = lambda s: [int(x) for x in s.split(",")]
     variants = []
@@ -59,17 +60,27 @@ def main():
     u = eng.to_device(0.1 * numpy.random.default_rng(0).standard_normal(n), pad=16)
     low = {0: lowering.lower_linear(lin(form_language), dim)}
     low[1] = low[2] = lowering.lower_nonlinear(nonlin(form_language), dim)
-    for q in ints(args.quantum):
+    # every (quantum, steering) mesh is built first; then, per mode, every (mesh, variant)
+    # pair is timed round-robin `reps` times: clocks and box state drift over a sweep (and from
+    # process to process), so alternatives are only ever compared on interleaved samples
+    built = []
+    for q, steer in [(q, s) for q in ints(args.quantum) for s in ints(args.steering)]:
+        os.environ["FVM_BANK_STEERING"] = str(steer)  # read when the mesh is tiled
         dm = engine.DeviceMesh(eng, mesh, need_el=False, tile_quantum=q)
+        data, vec = eng.alloc(8 * dm.nnz + 16), eng.alloc(8 * n + 16)
+        # (the vertex tables are bank-steered on a mesh's second launch, with the switch as it
+        # is set then: do those launches now)
+        k0 = eng.kernel(codegen.generate(low[0], 0, [None], [None], codegen.tuning(cdim)))
+        for _ in range(2):
+            dm.launch(k0, dirid=d_dir.ptr, u=u.ptr, data=data.ptr, vec=vec.ptr)
+        eng.sync()
         st = dm.stats()
-        print(st, f"tiles={dm.n_tiles} build_ms={dm.build_ms:.1f}", flush=True)
-        data = eng.alloc(8 * dm.nnz + 16)
-        vec = eng.alloc(8 * n + 16)
-        R = dm.n_halfedges / 2.0
-        for mode in ints(args.modes):
-            # build every variant first, then time them round-robin `reps` times: clocks and
-            # box state drift over a sweep, so variants are compared on interleaved samples
-            runs = []
+        print(f"steering={steer}", st, f"tiles={dm.n_tiles} build_ms={dm.build_ms:.1f}", flush=True)
+        built.append((f"q={st['quantum']} steer={steer}", dm, data, vec))
+    for mode in ints(args.modes):
+        runs = []
+        for label, dm, data, vec in built:
+            R = dm.n_halfedges / 2.0
             for tv in variants:
                 tune = codegen.tuning(cdim)
                 tune.update(tv)
@@ -90,7 +101,8 @@ def main():
                             lw, mode, [None] * len(lw.edge), [None] * len(lw.vertex), tune
                         )
                         k = eng.kernel(fun, fmad=bool(args.fmad))
-                        run = lambda k=k: dm.launch(k, dirid=d_dir.ptr, u=u.ptr, data=data.ptr, vec=vec.ptr)
+                        run = lambda k=k, dm=dm, data=data, vec=vec: dm.launch(
+                            k, dirid=d_dir.ptr, u=u.ptr, data=data.ptr, vec=vec.ptr)
                         alg = bench.algorithmic_bytes(
                             R, dm.nnz, n, dim, fun.uses_x, fun.uses_el,
                             "residual" if mode == 1 else "assembly",
@@ -100,24 +112,23 @@ def main():
                         run()
                     eng.sync()
                 except engine.FvmError as e:
-                    print(f"q={q} mode={mode} {tv}: FAILED {str(e)[:200]}", flush=True)
+                    print(f"{label} mode={mode} {tv}: FAILED {str(e)[:200]}", flush=True)
                     continue
-                runs.append((tv, run, alg, info, []))
-            for _ in range(args.reps):
-                for tv, run, alg, info, ms in runs:
-                    eng.timer_begin()
-                    for _ in range(args.steps):
-                        run()
-                    ms.append(eng.timer_end() / args.steps)
-            for tv, run, alg, info, ms in runs:
-                med, best = float(numpy.median(ms)), min(ms)
-                print(
-                    f"q={st['quantum']} mode={mode} {tv or 'default'}: median {med:.4f} ms (min {best:.4f})  "
-                    f"{alg / med / 1e6:.0f} GB/s alg  frac={alg / med / 1e6 / peak:.3f}  "
-                    f"regs={info.get('regs')} grid={info.get('grid')} smem={info.get('smem')}",
-                    flush=True,
-                )
-        del dm, data, vec
+                runs.append((label, tv, run, alg, info, []))
+        for _ in range(args.reps):
+            for label, tv, run, alg, info, ms in runs:
+                eng.timer_begin()
+                for _ in range(args.steps):
+                    run()
+                ms.append(eng.timer_end() / args.steps)
+        for label, tv, run, alg, info, ms in runs:
+            med, best = float(numpy.median(ms)), min(ms)
+            print(
+                f"{label} mode={mode} {tv or 'default'}: median {med:.4f} ms (min {best:.4f})  "
+                f"{alg / med / 1e6:.0f} GB/s alg  frac={alg / med / 1e6 / peak:.3f}  "
+                f"regs={info.get('regs')} grid={info.get('grid')} smem={info.get('smem')}",
+                flush=True,
+            )
 
 
 if __name__ == "__main__":
