@@ -251,7 +251,11 @@ int fvm_kernel_source(const char* functor_src, char* out, size_t out_len, size_t
  *   mode FVM_JACOBIAN : data_dev[nnz] written;       u_dev[n_vertices] read
  * vmask_dev / dirid_dev: per-vertex subdomain bits of the vertex terms and
  * 1-based index of the winning Dirichlet term (0 = free row); may be NULL when
- * the kernel was generated without them. */
+ * the kernel was generated without them.
+ * A triangle mesh's second launch (or its first residual / Jacobian / SpMV launch) first
+ * re-lays the tiles' vertex tables for shared-memory banks (a few ms, once; results are
+ * bit-identical; FVM_BANK_STEERING=0 turns it off).  FVM_TRACE=1 prints the host timeline
+ * of fvm_mesh_create and of that step on stderr. */
 int fvm_assemble(fvm_mesh* mesh, fvm_kernel* k, const uint8_t* vmask_dev,
                  const uint8_t* dirid_dev, const double* u_dev, double* data_dev,
                  double* vec_dev);
