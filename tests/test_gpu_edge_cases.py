@@ -455,3 +455,33 @@ def test_bank_steering_changes_no_bits(shuffle, monkeypatch):
         assert a.tobytes() == b.tobytes()
     if not shuffle:
         assert on[4] >= off[4]  # the steered tables stage a few extra vertices
+
+
+def test_error_in_a_subdomain_predicate_during_the_threaded_mesh_build():
+    """The device mesh is built on a helper thread while the main thread evaluates the
+    user's subdomain predicates: an exception there must surface as itself (after the build
+    thread was joined) and leave the engine usable."""
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import meshes
+
+    fl = eng.form_language
+
+    class Broken(fl.Subdomain if hasattr(fl, "Subdomain") else object):
+        is_boundary_only = True
+
+        def is_inside(self, x):
+            raise ValueError("predicate exploded")
+
+    class P:
+        def apply(self, u):
+            return fl.integrate(lambda x: -fl.n_dot_grad(u(x)), fl.dS) - fl.integrate(lambda x: 1.0, fl.dV)
+
+        def dirichlet(self, u):
+            return [(u, Broken())]
+
+    mesh = meshes.Mesh(*problems.rectangle(61, 47))
+    with pytest.raises(ValueError, match="predicate exploded"):
+        eng.discretize_linear(P(), mesh)
+    A, b = eng.discretize_linear(problems.poisson(fl), mesh)  # same mesh object, engine intact
+    A2, b2 = eng.discretize_linear(problems.poisson(fl), meshes.Mesh(*problems.rectangle(61, 47)))
+    assert A.data.tobytes() == A2.data.tobytes() and b.tobytes() == b2.tobytes()
