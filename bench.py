@@ -378,7 +378,7 @@ def leg_c5(args, D, N):
                 "seconds": time.time() - ts,
                 "newton_steps": steps,
                 "linear_iterations": lin_its,
-                "spmv_per_iteration": 1 if method == "cg" else 2,
+                "spmv_per_iteration": 2 if method == "bicgstab" else (int(method[7:]) if method.startswith("cg-cheb") else 1),
                 "tol": args.newton_tol,
                 "max_u": umax,
                 "what": f"pyfvm.newton from u = 0 with a Jacobi-{method} jacobian_solver, residual / "

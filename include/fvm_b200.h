@@ -331,11 +331,23 @@ int fvm_bicgstab_dist(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* val
  * device-resident scalars, two iterations per replayed CUDA graph.  Starts from the Jacobi
  * guess x0 = b / diag(A), which solves pyfvm's Dirichlet rows (identity rows whose columns are
  * NOT eliminated) exactly and so keeps them out of the Krylov space.  dist == NULL: one GPU;
- * otherwise the row partition of fvm_bicgstab_dist.  work_dev: 4 * ((n + 1) & ~1) + 16
+ * otherwise the row partition of fvm_bicgstab_dist.  work_dev: 7 * ((n + 1) & ~1) + 16
  * doubles.  Fails with "CG breakdown" when p.Ap and r.(r/d) differ in sign. */
 int fvm_cg(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* values_dev, const double* b_dev,
            double* x_dev, double* work_dev, double tol, int maxiter, int check_every,
            const fvm_dist_args* dist_or_null, int* iters_out, double* relres_out);
+/* The same with a stronger preconditioner (SURVEY 8f rank 2 asks for more than Jacobi; the
+ * README points at AMG [README.md:67-77], which is out of scope): z = p(D^-1 A) D^-1 r with
+ * the Chebyshev polynomial of degree `degree` on [lambda_max / 30, lambda_max] -- degree - 1
+ * more SpMVs per iteration and no more reductions, i.e. fewer, fatter iterations where an
+ * iteration is bound by its rank-wide synchronisations.  lambda_max: an upper bound of the
+ * spectrum of D^-1 A, e.g. fvm_csr_gershgorin (max over all ranks).  degree 1 = fvm_cg. */
+int fvm_cg_poly(fvm_mesh* mesh, fvm_kernel* spmv_kernel, const double* values_dev,
+                const double* b_dev, double* x_dev, double* work_dev, double tol, int maxiter,
+                int check_every, int degree, double lambda_max, const fvm_dist_args* dist_or_null,
+                int* iters_out, double* relres_out);
+/* max_i sum_j |a_ij| / |a_ii| over this mesh's rows (Gershgorin's bound for D^-1 A) */
+int fvm_csr_gershgorin(fvm_mesh* mesh, const double* values_dev, double* out);
 
 /* ---- small device helpers used around the path --------------------------------*/
 /* deterministic ||x||_2 (fixed-shape two-stage reduction) [README.md:121 newton] */

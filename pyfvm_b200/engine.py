@@ -171,6 +171,12 @@ SYMBOLS = {
     ),
     "fvm_device_cache_stats": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     "fvm_device_cache_flush": (c_int, [c_void_p]),
+    "fvm_cg_poly": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int,
+         c_int, c_double, c_void_p, POINTER(c_int), POINTER(c_double)],
+    ),
+    "fvm_csr_gershgorin": (c_int, [c_void_p, c_void_p, POINTER(c_double)]),
     "fvm_cg": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int, c_int,

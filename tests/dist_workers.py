@@ -200,6 +200,18 @@ def gpu_worker():
             print(f"distributed CG: its={its_c} relres={rel_c:.2e}; max diff to BiCGStab {dc:.2e}; "
                   f"repeatable bits: ok={good}", flush=True)
         ok &= good
+        # the Chebyshev-preconditioned variant (3 halo exchanges per iteration, an odd number:
+        # the buffer parity bookkeeping of the captured graph is exercised)
+        xd = dp.eng.alloc(8 * max(1, part.n_owned) + 16)
+        its_p, rel_p = sysm.cg(dp.F.ptr, xd.ptr, tol=1e-10, degree=3)
+        xp = numpy.empty(part.n_owned)
+        xd.download(xp)
+        dpp = float(numpy.abs(xp - xs[1][2]).max()) if part.n_owned else 0.0
+        good = rel_p <= 1e-10 and dpp <= 1e-7 * max(scale, 1e-30) and its_p < its_c
+        if rank == 0:
+            print(f"distributed CG + Chebyshev(3): its={its_p} (Jacobi: {its_c}) relres={rel_p:.2e}; "
+                  f"max diff to BiCGStab {dpp:.2e}: ok={good}", flush=True)
+        ok &= good
         dist.barrier()
         sysm.close()
         dp.halo.close()

@@ -188,3 +188,28 @@ def test_device_newton_with_cg():
     assert numpy.abs(u_c - u_b).max() <= 1e-8
     u_cb = pyfvm.newton(f.eval, solvers.jacobian_solver(jacobian, method="cg"), numpy.zeros(n), verbose=False)
     assert numpy.abs(u_cb - u_b).max() <= 1e-8
+
+
+@pytest.mark.parametrize("name,kind,args", [("poisson", "rect", (201, 101)), ("robin", "rect", (121, 77)),
+                                            ("poisson", "cube", (21,))])
+def test_chebyshev_preconditioned_cg(name, kind, args):
+    """fvm_cg_poly: the Chebyshev polynomial of D^-1 A as preconditioner -- the same solution
+    in 2.5-4 times fewer iterations (reductions) for about the same number of SpMVs."""
+    import pyfvm_b200 as eng
+    from pyfvm_b200 import problem, solvers
+
+    mesh = _mesh(kind, *args)
+    lp = problem.LinearProblem(getattr(problems, name)(eng.form_language), mesh)
+    A, b = lp.assemble()
+    u_ref = linalg.spsolve(A.tocsc(), b)
+    u1, it1, _ = solvers.solve_linear(lp, tol=1e-11, method="cg")
+    sysm = solvers.DeviceSystem(lp.dmesh, lp.data.ptr)
+    lmax = sysm._lambda_max()
+    assert lmax == pytest.approx((abs(A) @ numpy.ones(lp.n) / abs(A.diagonal())).max(), rel=1e-12)
+    for degree in (2, 4):
+        u, it, relres = solvers.solve_linear(lp, tol=1e-11, method=f"cg-cheb{degree}")
+        assert relres <= 1e-11
+        assert numpy.abs(u - u_ref).max() <= 1e-8 * numpy.abs(u_ref).max()
+        assert it * degree <= 1.5 * it1 + 8 and it <= 0.75 * it1 + 2  # fewer, fatter iterations
+        u2, it2, _ = solvers.solve_linear(lp, tol=1e-11, method=f"cg-cheb{degree}")
+        assert it2 == it and u2.tobytes() == u.tobytes()
