@@ -927,8 +927,9 @@ def main():
                     help="c4 run: points per side of the config-5-family leg (0: skip)")
     ap.add_argument("--cube", type=int, default=200, help="points per side of the c5 cube")
     ap.add_argument("--solve", action="store_true", help="c5: also run the full Newton solve")
-    ap.add_argument("--linear-solver", default="bicgstab,cg",
-                    help="c5 --solve: comma list of the device Krylov solvers to time (bicgstab, cg)")
+    ap.add_argument("--linear-solver", default="bicgstab,cg,cg-cheb3",
+                    help="c5 --solve: comma list of the device Krylov solvers to time "
+                    "(bicgstab, cg, cg-cheb<degree>)")
     ap.add_argument("--newton-tol", type=float, default=1e-10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
